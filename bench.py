@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py - headline measurement of the RAG diffusion sampling path.
+
+Metric (BASELINE.json): denoising-steps/sec at TED shape, B=512 clips per GPU, T=1000
+ancestral schedule, classifier-free guidance on (one step = the whole batch advanced one
+timestep = 2 denoiser passes per clip + guidance + posterior update).
+
+    python bench.py --gpus 1 --steps 200 --warmup 20
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29511 bench.py --gpus 8 --steps 200 --warmup 20
+    python bench.py --impl reference --steps 3 --warmup 1      # CPU arm (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_SAMPLE_STEP = {"ted": 337207296, "beat": 400027648}   # BASELINE.md section 3 (algorithmic, CFG = 2 passes)
+T_FULL = 1000
+
+
+def model_args(dims):
+    return types.SimpleNamespace(mdm_condm='text', latent_dim=512, ff_size=1024, layers=dims.layers,
+                                 cond_mask_prob=0.1, arch='trans_enc', emb_trans_dec=False, dataset='humanml',
+                                 lang_model=None, mlpact='silu', diffusion_steps=T_FULL, noise_schedule='cosine',
+                                 sigma_small=True, lambda_vel=1.0, lambda_rcxyz=0.0, lambda_fc=0.0,
+                                 njoints=dims.njoints)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_port_steps_per_s(dims, batch_equiv, n_steps, warmup, sample_batch, threads):
+    """The oracle (a port of the reference's CPU path) timed on the host cores.
+    One oracle step at `sample_batch` clips, scaled to steps/s at `batch_equiv` clips
+    (steps are iso-cost per clip on CPU at these sizes: BASELINE.md section 4)."""
+    import torch
+    from livelyspeaker_b200 import synthetic
+    from oracle import sampler_oracle, schedule_oracle
+    torch.set_num_threads(threads)
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    tab, tmap = schedule_oracle.build("cosine", T_FULL, "")
+    y = synthetic.synth_cond(dims, sample_batch)
+    tape = sampler_oracle.NoiseTape(seed=0)
+    x = tape.draw(sample_batch, dims.njoints, dims.nfeats, 34)
+    times = []
+    with torch.no_grad():
+        for k in range(warmup + n_steps):
+            t0 = time.perf_counter()
+            x, _ = sampler_oracle.p_sample_step(sd, tab, tmap, x, T_FULL - 1 - k, y, tape, dims.njoints, dims.nfeats)
+            if k >= warmup:
+                times.append(time.perf_counter() - t0)
+    per_step = sum(times) / len(times)
+    return (sample_batch / batch_equiv) / per_step, per_step
+
+
+def run_reference_arm(a, dims, rank):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference
+    tree is not present on the GPU box, so this times oracle/ (kind "port"), which is
+    pinned to the reference draw-by-draw (tests/golden/PIN_REPORT.json)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_steps = max(1, min(a.steps, 6))
+    sample_batch = 32
+    value, per_step = cpu_port_steps_per_s(dims, a.batch, n_steps, max(1, min(a.warmup, 1)), sample_batch, threads)
+    sample = "%d oracle p_sample steps at B=%d clips (CFG on), %.3f s each, scaled to B=%d" % (
+        n_steps, sample_batch, per_step, a.batch)
+    line = {"impl": "reference", "metric": "denoising-steps/sec", "value": value * a.gpus,
+            "unit": "steps/s (1 step = %d clips advanced one timestep, CFG on)" % a.batch, "n_gpus": a.gpus,
+            "steps": n_steps, "warmup": 1, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, dims),
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value * a.gpus, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "clips_per_s": value * a.gpus * a.batch / T_FULL}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, dims):
+    return {"workload": "TED RAG sampling B=%d/GPU, F=34, J*D=%d, T=%d ancestral, 8-layer/512-d, CFG scale 1.5"
+                        % (a.batch, dims.jd, T_FULL) if dims.dataset == "ted" else
+                        "BEAT RAG sampling B=%d/GPU, F=34, J*D=%d, T=%d ancestral" % (a.batch, dims.jd, T_FULL),
+            "global_batch": a.batch * a.gpus, "timesteps": T_FULL, "sampler": a.sampler,
+            "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
+            "parallelism": "batch shard x%d, no per-step collective, 1 all_gather at loop end" % a.gpus}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "simt", "tc_bf16x3", "tc_bf16"])
+    ap.add_argument("--dataset", default="ted", choices=["ted", "beat"])
+    ap.add_argument("--batch", type=int, default=512, help="clips per GPU")
+    ap.add_argument("--sampler", default="ancestral", choices=["ancestral", "ddim"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from livelyspeaker_b200 import synthetic
+    dims = synthetic.dims_for(a.dataset)
+    if a.impl == "reference":
+        run_reference_arm(a, dims, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import livelyspeaker_b200 as ls
+    from livelyspeaker_b200 import beat_model_util, sharding
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == a.gpus, "WORLD_SIZE %d != --gpus %d (launch with torch.distributed.run)" % (world, a.gpus)
+
+    B, K, W = a.batch, a.steps, a.warmup
+    ddim = a.sampler == "ddim"
+    mk = beat_model_util.create_model_and_diffusion if a.dataset == "beat" else ls.create_model_and_diffusion
+    model, diffusion = mk(model_args(dims), "")
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    model.load_state_dict(sd, strict=True)
+    model.set_impl(a.kernel)
+    cfg = ls.ClassifierFreeSampleModel(model).to(dev).eval()
+    eng = model.engine(B)
+    shape = (B, dims.njoints, dims.nfeats, 34)
+
+    # conditioning of this rank's shard of the global batch (seed differs per rank)
+    y_host = synthetic.synth_cond(dims, B, seed=233 + rank)
+    y_pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in y_host.items()}
+    y_dev = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in y_host.items()}
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    torch.manual_seed(1000 + rank)
+
+    # ------------------------------------------------------------------ device-resident steps
+    eng.set_cond(y_dev, force=True)
+    scale = y_dev["scale"].float().contiguous()
+    x = torch.randn(*shape, device=dev)
+    perm_like = torch.empty(34, B, dims.njoints, dims.nfeats, device=dev).permute(1, 2, 3, 0)
+    idx = [T_FULL - 1 - (k % T_FULL) for k in range(W + K)]
+    params = [diffusion.step_params(i, ddim=ddim, eta=0.0, clip_denoised=False) for i in idx]
+
+    def one_step(k, x_in):
+        e_c = torch.randn(B, 1, 512, device=dev)
+        e_u = torch.randn(B, 1, 512, device=dev)
+        nz = torch.randn_like(perm_like)
+        x_out = torch.empty_like(x_in)
+        eng.step(params[k], x_in, e_c, e_u, nz, scale, x_out, None)
+        return x_out
+
+    for k in range(W):
+        x = one_step(k, x)
+    sync_all()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    sync_all()
+    for k in range(K):
+        flush_buf.zero_()                      # evict L2 (126 MB) - outside the event bracket
+        ev[k][0].record()
+        x = one_step(W + k, x)
+        ev[k][1].record()
+    sync_all()
+    launches = eng.launch_count() - launches0
+    clk = clocks.stop()
+    t_ms = sum(s.elapsed_time(e) for s, e in ev)
+    assert torch.isfinite(x).all(), "sampler diverged"
+
+    # dominant kernel alone (the ls_step launch without the torch RNG launches), for the roofline
+    g = torch.Generator(device=dev).manual_seed(5)
+    e_c = torch.randn(B, 1, 512, device=dev, generator=g)
+    e_u = torch.randn(B, 1, 512, device=dev, generator=g)
+    nz = torch.randn(*shape, device=dev, generator=g)
+    x_out = torch.empty_like(x)
+    kk = min(K, 50)
+    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(kk)]
+    l0 = eng.launch_count()
+    for k in range(kk):
+        flush_buf.zero_()
+        evk[k][0].record()
+        eng.step(params[W + k], x, e_c, e_u, nz, scale, x_out, None)
+        evk[k][1].record()
+    torch.cuda.synchronize()
+    kern_ms = sum(s.elapsed_time(e) for s, e in evk) / kk
+    launches_per_step = (eng.launch_count() - l0) / kk
+
+    # ------------------------------------------------------------------ end to end (host buffers)
+    n_e2e = min(K, T_FULL)
+    h2d = sum(v.numel() * v.element_size() for k_, v in y_pinned.items()
+              if torch.is_tensor(v) and k_ in ("audio_input", "origin_x", "vid_indices", "scale", "emo"))
+    sample_fn = diffusion.ddim_sample_loop if ddim else diffusion.p_sample_loop
+
+    def e2e_once():
+        yk = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in y_pinned.items()}
+        if world > 1:
+            local = sample_fn(cfg, shape, clip_denoised=False, model_kwargs={"y": yk}, skip_timesteps=T_FULL - n_e2e)
+            out = sharding.all_gather_samples(local, B * world)[rank * B:(rank + 1) * B]
+        else:
+            out = sample_fn(cfg, shape, clip_denoised=False, model_kwargs={"y": yk}, skip_timesteps=T_FULL - n_e2e)
+        return out.to("cpu", non_blocking=False)
+
+    e2e_once() if n_e2e <= 50 else None       # warm-up of the e2e path when it is cheap
+    sync_all()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    s_ev.record()
+    res = e2e_once()
+    e_ev.record()
+    sync_all()
+    e2e_ms = max(s_ev.elapsed_time(e_ev), (time.perf_counter() - t0) * 1e3 if world == 1 else 0.0)
+    d2h = res.numel() * res.element_size()
+
+    # ------------------------------------------------------------------ reduce over ranks
+    stats = torch.tensor([t_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    t_ms, e2e_ms, kern_ms = [float(v) for v in stats.tolist()]
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        steps_per_s = world * K / (t_ms / 1e3)
+        flop_step = B * FLOP_PER_SAMPLE_STEP[a.dataset]
+        achieved = flop_step / (kern_ms / 1e3) / 1e12
+        impl = eng.get_impl()
+        line = {
+            "metric": "denoising-steps/sec", "value": steps_per_s,
+            "unit": "steps/s (1 step = %d clips advanced one timestep, CFG on)" % B,
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"simt": "f32", "tc_bf16x3": "bf16x3 split operands, f32 accumulate",
+                      "tc_bf16": "bf16 operands, f32 accumulate"}[impl],
+            "data": "synthetic", "config": workload_config(a, dims), "impl": "ours", "kernel": impl,
+            "clips_per_s": steps_per_s * B / T_FULL,
+            "e2e": {"value": world * n_e2e / (e2e_ms / 1e3), "unit": "steps/s", "steps_in_loop": n_e2e,
+                    "h2d_bytes_per_step": h2d / n_e2e, "d2h_bytes_per_step": d2h / n_e2e,
+                    "what": "p_sample_loop(model, shape, model_kwargs=pinned host cond) -> .cpu(): H2D of the cond, "
+                            "WavEncoder + cond precompute, %d steps, D2H of the samples" % n_e2e},
+            "gpu_launches": launches,
+            "launches_per_step": launches_per_step,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": kern_ms, "flop_per_launch": flop_step,
+                         "note": "algorithmic flops (BASELINE.md section 3): x3 of the bf16x3 split and padding not counted"},
+            "clocks": clk,
+        }
+        if not a.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            v, per = cpu_port_steps_per_s(dims, B, 3, 1, 32, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
+                                    "sample": "3 oracle p_sample steps at B=32 clips (CFG on), %.3f s each, "
+                                              "scaled to B=%d" % (per, B)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,169 @@
+/*
+ * livelyspeaker_b200.h - C ABI of the B200-native RAG sampling path.
+ *
+ * The reference (zyhbili/LivelySpeaker @ 7f6ccd1) is pure Python/PyTorch and has
+ * no FFI of its own; this header is therefore the boundary a
+ * maintainer would bind with ctypes from the reference's Python call sites.
+ * Each entry point names the reference code it replaces.  INTEGRATION.md shows
+ * the ctypes stubs.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative LS_E* code on failure;
+ *     ls_last_error() gives the message.  No exceptions cross the ABI.
+ *   - all tensor pointers are DEVICE pointers on the handle's device unless the
+ *     parameter name ends in _host; fp32 unless stated; layouts are the
+ *     reference's logical layouts, dense, row-major unless strides are passed.
+ *   - calls are asynchronous on the given stream (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream).  No allocation happens after
+ *     ls_create(): workspaces sized for cfg.max_batch live in the handle.
+ *   - one handle per GPU per model; a handle is not thread-safe.
+ */
+#ifndef LIVELYSPEAKER_B200_H
+#define LIVELYSPEAKER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS_ABI_VERSION 1
+
+enum {
+  LS_OK = 0,
+  LS_EINVAL = -1,   /* bad argument / shape mismatch            */
+  LS_ESTATE = -2,   /* call order violated (weights, cond, ...) */
+  LS_ECUDA = -3,    /* a CUDA runtime call failed               */
+  LS_ENOMEM = -4,
+  LS_EUNSUPPORTED = -5
+};
+
+typedef struct ls_handle ls_handle;
+
+/* Model geometry.  TED: njoints 9, nfeats 3, n_pre_emb 1, audio_len 36267.
+ * BEAT: 47, 6, 2 (style + emotion token), 36266.
+ * scripts/mdm_utils/model_util.py:20-37, scripts/model/RAG.py:17-74,
+ * scripts_beat/model/RAG.py:56,72-74. */
+typedef struct ls_config {
+  int32_t njoints;
+  int32_t nfeats;
+  int32_t n_frames;      /* must be 34: fixed by Conv1d(S,S,1) + WavEncoder strides */
+  int32_t n_pre_emb;     /* 1 (TED) or 2 (BEAT)                                     */
+  int32_t latent_dim;    /* must be 512 in this build                               */
+  int32_t n_layers;      /* MLPblock count, <= 16                                   */
+  int32_t audio_len;     /* samples per clip; WavEncoder must map it to n_frames    */
+  int32_t n_speakers;    /* rows of speaker_embedding (1400)                        */
+  int32_t n_emotions;    /* rows of emotion_embedding (8), 0 for TED                */
+  int32_t max_batch;     /* workspaces are sized for this many clips                */
+  int32_t max_timestep;  /* time-embedding table covers original t in [0, this)     */
+  int32_t device;        /* CUDA device ordinal                                     */
+} ls_config;
+
+/* Sampler update applied after the guided x0 prediction.
+ *   mode 0, ancestral  (gaussian_diffusion.py:260-282, 507-558):
+ *       x_prev = c[0]*x0 + c[1]*x_t + add_noise * exp(0.5*c[2]) * noise
+ *       c = { posterior_mean_coef1[i], posterior_mean_coef2[i],
+ *             posterior_log_variance_clipped[i] }               (fp64 -> fp32 casts)
+ *   mode 1, DDIM       (gaussian_diffusion.py:418-422, 745-798):
+ *       eps    = (c[0]*x_t - x0) / c[1]
+ *       x_prev = x0*c[2] + c[3]*eps + add_noise * c[4] * noise
+ *       c = { sqrt_recip_alphas_cumprod[i], sqrt_recipm1_alphas_cumprod[i],
+ *             sqrt(abar_prev), sqrt(1-abar_prev-sigma^2), sigma }  (fp32)
+ *   mode 2: no update, only pred_x0 is written (p_mean_variance callers). */
+typedef struct ls_step_params {
+  int32_t mode;
+  int32_t t_model;        /* ORIGINAL timestep fed to the denoiser = timestep_map[i]
+                             (respace.py:118-130)                                     */
+  int32_t clip_denoised;  /* clamp x0 to [-1,1] (gaussian_diffusion.py:365-371)       */
+  int32_t add_noise;      /* (i != 0)                                                 */
+  float c[8];
+} ls_step_params;
+
+/* Which implementation ls_step / ls_cfg_forward use for the denoiser. */
+enum {
+  LS_IMPL_AUTO = 0,       /* fused tcgen05 kernel when built in, else simt            */
+  LS_IMPL_SIMT = 1,       /* fp32 CUDA-core kernels (exact-order reference on device) */
+  LS_IMPL_TC_BF16X3 = 2,  /* tcgen05, bf16 hi/lo split operands, fp32 accumulate      */
+  LS_IMPL_TC_BF16 = 3     /* tcgen05, plain bf16 operands (fast mode, looser parity)  */
+};
+
+int ls_abi_version(void);
+const char* ls_last_error(const ls_handle* h); /* h may be NULL: error of the last failed ls_create */
+
+/* RAG.__init__ (scripts/model/RAG.py:17-74): allocates weights + workspaces. */
+int ls_create(ls_handle** out, const ls_config* cfg);
+void ls_destroy(ls_handle* h);
+
+/* load_model_wo_clip / load_state_dict (scripts/mdm_utils/model_util.py:5-10):
+ * one call per state_dict entry, reference key names and shapes, fp32, device
+ * memory.  Unknown keys -> LS_EINVAL (the reference asserts no unexpected keys);
+ * `clip_model.*` and the three `pe` buffers are accepted and ignored/used.       */
+int ls_load_weight(ls_handle* h, const char* key, const float* dev_ptr,
+                   const int64_t* shape, int32_t ndim, void* stream);
+/* Checks that every required key arrived, derives the kernel-side layouts
+ * (transposed / bf16 hi+lo / padded copies) and the time-embedding table
+ * emb[t] = time_embed(pe[t]) (scripts/model/mlp_module.py:123-136).              */
+int ls_finalize_weights(ls_handle* h, void* stream);
+
+int ls_set_impl(ls_handle* h, int32_t impl);
+int ls_get_impl(const ls_handle* h);   /* resolved implementation (never AUTO) */
+
+/* Everything in RAG.forward that does not depend on x_t / t
+ * (scripts/model/RAG.py:106-120): WavEncoder (audio_enc.py:6-25), the audio /
+ * prefix halves of input_mapping, speaker mu / logvar, BEAT emotion token.
+ * origin_x: [B, J*D, F]; frames >= 4 are ignored and, when mutate_origin != 0,
+ * zeroed in place like RAG.py:110 does to the caller's tensor.
+ * emo may be NULL (TED); emo_stride is the element stride between clips
+ * (the reference reads y['emo'][:, 0]).                                          */
+int ls_precompute_cond(ls_handle* h, int32_t B, const float* audio, float* origin_x,
+                       const int64_t* vid_indices, const int64_t* emo, int64_t emo_stride,
+                       int32_t mutate_origin, void* stream);
+
+/* WavEncoder.forward alone (scripts/model/audio_enc.py:22-25): [B,L] -> [B,34,256]. */
+int ls_wav_encoder(ls_handle* h, int32_t B, const float* audio, float* out, void* stream);
+
+/* RAG.forward (scripts/model/RAG.py:98-133) on the cond set up by
+ * ls_precompute_cond.  t: ORIGINAL timesteps, one per clip.  uncond != 0 zeroes the
+ * audio embedding (mask_cond force_mask, RAG.py:80-83).  style_eps [B,512] is the
+ * randn of reparameterize (RAG.py:10-13).  out [B,J*D,F]; z_mu / z_logvar [B,512]
+ * may be NULL.                                                                    */
+int ls_model_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t,
+                     int32_t uncond, const float* style_eps, float* out,
+                     float* z_mu, float* z_logvar, void* stream);
+
+/* ClassifierFreeSampleModel.forward (scripts/model/cfg_sampler.py:24-31):
+ * out = out_u + scale[b] * (out_c - out_u).                                       */
+int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t,
+                   const float* eps_cond, const float* eps_uncond, const float* scale,
+                   float* out, void* stream);
+
+/* One denoising step with a batch-uniform timestep: _WrappedModel +
+ * ClassifierFreeSampleModel + RAG + p_mean_variance + p_sample / ddim_sample
+ * (respace.py:118-130, cfg_sampler.py:24-31, RAG.py:98-133,
+ * gaussian_diffusion.py:284-399, 507-558, 745-798).
+ * noise is addressed as noise[b*noise_sb + jd*noise_sj + f*noise_sf] so the
+ * reference's memory-order draw (DESIGN.md "RNG layout") can be passed as is;
+ * noise_sb = 0 implements const_noise.  x_prev / pred_x0 are dense [B,J*D,F];
+ * x_prev may alias x_t; pred_x0 may be NULL.                                     */
+int ls_step(ls_handle* h, int32_t B, const ls_step_params* p, const float* x_t,
+            const float* eps_cond, const float* eps_uncond, const float* noise,
+            int64_t noise_sb, int64_t noise_sj, int64_t noise_sf, const float* scale,
+            float* x_prev, float* pred_x0, void* stream);
+
+/* q_sample (gaussian_diffusion.py:240-258): out = c_x0*x0 + c_noise*noise, n elements. */
+int ls_q_sample(ls_handle* h, int64_t n, const float* x0, const float* noise,
+                float c_x0, float c_noise, float* out, void* stream);
+
+/* Introspection used by tests / bench: number of kernels launched by this handle
+ * since creation, and read-back of the step-invariant buffers.                    */
+int64_t ls_launch_count(const ls_handle* h);
+/* which: 0 = A (audio proj) [B,34,512], 1 = P (prefix proj) [B,34,512],
+ *        2 = z_mu [B,512], 3 = z_logvar [B,512], 4 = emb table [max_timestep,512] */
+/* Copies min(capacity, n) floats into dst (device memory) and stores n in *n_elems.    */
+int ls_debug_buffer(ls_handle* h, int32_t which, float* dst, int64_t capacity, int64_t* n_elems,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIVELYSPEAKER_B200_H */

@@ -1,0 +1,270 @@
+"""ctypes binding of libls_b200.so (include/livelyspeaker_b200.h) and the `Engine`
+object the Python mirror of the reference interface drives.
+
+There is deliberately NO fallback: if the shared library is missing or the
+device is not a CUDA sm_100 GPU, every compute entry point raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, byref, c_char_p, c_float, c_int32, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libls_b200.so")
+
+LS_IMPL_AUTO, LS_IMPL_SIMT, LS_IMPL_TC_BF16X3, LS_IMPL_TC_BF16 = 0, 1, 2, 3
+IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
+
+EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
+           "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
+           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_q_sample", "ls_launch_count",
+           "ls_debug_buffer"]
+
+
+class LsConfig(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("njoints", "nfeats", "n_frames", "n_pre_emb", "latent_dim", "n_layers",
+                                       "audio_len", "n_speakers", "n_emotions", "max_batch", "max_timestep",
+                                       "device")]
+
+
+class LsStepParams(ctypes.Structure):
+    _fields_ = [("mode", c_int32), ("t_model", c_int32), ("clip_denoised", c_int32), ("add_noise", c_int32),
+                ("c", c_float * 8)]
+
+
+class LsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libls_b200.so once; raise (never fall back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LsError("%s not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.ls_abi_version.restype = c_int32
+    lib.ls_last_error.restype = c_char_p
+    lib.ls_last_error.argtypes = [c_void_p]
+    lib.ls_create.argtypes = [POINTER(c_void_p), POINTER(LsConfig)]
+    lib.ls_destroy.argtypes = [c_void_p]
+    lib.ls_destroy.restype = None
+    lib.ls_load_weight.argtypes = [c_void_p, c_char_p, c_void_p, POINTER(c_int64), c_int32, c_void_p]
+    lib.ls_finalize_weights.argtypes = [c_void_p, c_void_p]
+    lib.ls_set_impl.argtypes = [c_void_p, c_int32]
+    lib.ls_get_impl.argtypes = [c_void_p]
+    lib.ls_precompute_cond.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int32, c_void_p]
+    lib.ls_wav_encoder.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.ls_model_forward.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]
+    lib.ls_cfg_forward.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]
+    lib.ls_step.argtypes = [c_void_p, c_int32, POINTER(LsStepParams), c_void_p, c_void_p, c_void_p, c_void_p,
+                            c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ls_q_sample.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]
+    lib.ls_launch_count.argtypes = [c_void_p]
+    lib.ls_launch_count.restype = c_int64
+    lib.ls_debug_buffer.argtypes = [c_void_p, c_int32, c_void_p, c_int64, POINTER(c_int64), c_void_p]
+    if lib.ls_abi_version() != 1:
+        raise LsError("ABI version mismatch: library %d, binding 1" % lib.ls_abi_version())
+    _lib = lib
+    return lib
+
+
+def _f32(t, device):
+    """Dense fp32 tensor on `device` (pinned host tensors are copied asynchronously)."""
+    if t.device != device:
+        t = t.to(device, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    """One ls_handle: weights + workspaces for one model on one GPU."""
+
+    def __init__(self, dims, device, max_batch=512, max_timestep=1000, n_speakers=1400, n_emotions=0):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise LsError("livelyspeaker_b200 computes on CUDA sm_100a only (got device %s); "
+                          "there is no CPU path" % device)
+        self.lib = load_library()
+        self.dims = dims
+        self.device = device
+        self.max_batch = int(max_batch)
+        self.max_timestep = int(max_timestep)
+        self.cfg = LsConfig(dims.njoints, dims.nfeats, 34, dims.n_pre_emb, dims.latent_dim, dims.layers,
+                            dims.audio_len, n_speakers, n_emotions, self.max_batch, self.max_timestep,
+                            device.index if device.index is not None else torch.cuda.current_device())
+        self.h = c_void_p()
+        rc = self.lib.ls_create(byref(self.h), byref(self.cfg))
+        if rc != 0:
+            raise LsError("ls_create failed (%d): %s" % (rc, self.lib.ls_last_error(None).decode()))
+        self._weights_sig = None
+        self._cond_sig = None
+        self._cond_keep = None
+        self._impl = LS_IMPL_AUTO
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None) and self.h.value:
+                self.lib.ls_destroy(self.h)
+                self.h = c_void_p()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LsError("libls_b200 error %d: %s" % (rc, self.lib.ls_last_error(self.h).decode()))
+
+    # ---- weights -----------------------------------------------------------------
+    def load_state_dict(self, sd):
+        """sd: reference-named tensors (any device); uploads + derives kernel layouts."""
+        with torch.cuda.device(self.device):
+            keep = []
+            for key, val in sd.items():
+                if not torch.is_tensor(val):
+                    continue
+                if key.endswith("sequence_pos_encoder.pe") and key != "backbone.embed_timestep.sequence_pos_encoder.pe":
+                    continue
+                t = _f32(val.detach(), self.device)
+                keep.append(t)
+                shape = (c_int64 * t.dim())(*t.shape)
+                self._check(self.lib.ls_load_weight(self.h, key.encode(), c_void_p(t.data_ptr()), shape, t.dim(),
+                                                    _stream()))
+            self._check(self.lib.ls_finalize_weights(self.h, _stream()))
+            self._check(self.lib.ls_set_impl(self.h, self._impl))
+            torch.cuda.current_stream().synchronize()   # `keep` may be freed after this
+        self._cond_sig = None
+
+    def set_impl(self, impl):
+        impl = IMPL_NAMES[impl] if isinstance(impl, str) else int(impl)
+        self._check(self.lib.ls_set_impl(self.h, impl))
+        self._impl = impl
+
+    def get_impl(self):
+        v = self.lib.ls_get_impl(self.h)
+        return {v_: k for k, v_ in IMPL_NAMES.items()}[v]
+
+    def launch_count(self):
+        return int(self.lib.ls_launch_count(self.h))
+
+    # ---- conditioning ---------------------------------------------------------------
+    @staticmethod
+    def _sig(y):
+        sig = []
+        for k in ("audio_input", "origin_x", "vid_indices", "emo"):
+            t = y.get(k)
+            sig.append(None if t is None else (t.data_ptr(), t._version, tuple(t.shape), str(t.device)))
+        return tuple(sig)
+
+    def set_cond(self, y, force=False):
+        """ls_precompute_cond on y (cached on tensor identity + version).  Zeroes
+        y['origin_x'][..., 4:] in the caller's tensor like RAG.py:110."""
+        sig = self._sig(y)
+        if not force and sig == self._cond_sig:
+            return
+        audio = _f32(y["audio_input"], self.device)
+        B = audio.shape[0]
+        if B > self.max_batch:
+            raise LsError("batch %d exceeds the engine's max_batch %d" % (B, self.max_batch))
+        ox_user = y["origin_x"]
+        inplace = (ox_user.device == self.device and ox_user.dtype == torch.float32 and ox_user.is_contiguous())
+        ox = ox_user if inplace else _f32(ox_user, self.device).clone()
+        vid = y["vid_indices"].to(self.device, non_blocking=True).long().contiguous()
+        emo, emo_ptr, emo_stride = None, None, 0
+        if self.dims.n_pre_emb == 2:
+            emo = y["emo"].to(self.device, non_blocking=True).long()
+            emo_ptr, emo_stride = c_void_p(emo.data_ptr()), emo.stride(0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_precompute_cond(self.h, B, c_void_p(audio.data_ptr()), c_void_p(ox.data_ptr()),
+                                                    c_void_p(vid.data_ptr()), emo_ptr, emo_stride, 1, _stream()))
+        if not inplace:
+            ox_user[..., 4:] = 0          # keep the reference's visible side effect
+        self._cond_keep = (audio, ox, vid, emo)
+        self._cond_sig = self._sig(y)
+        self.cond_batch = B
+
+    def debug_buffer(self, which):
+        """0 = A, 1 = P, 2 = z_mu, 3 = z_logvar, 4 = time-embedding table (flat fp32 copies)."""
+        n = c_int64()
+        self._check(self.lib.ls_debug_buffer(self.h, which, None, 0, byref(n), _stream()))
+        out = torch.empty(n.value, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_debug_buffer(self.h, which, c_void_p(out.data_ptr()), n.value, byref(n), _stream()))
+        return out
+
+    # ---- compute ----------------------------------------------------------------------
+    def wav_encoder(self, audio):
+        audio = _f32(audio, self.device)
+        out = torch.empty(audio.shape[0], 34, 256, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_wav_encoder(self.h, audio.shape[0], c_void_p(audio.data_ptr()),
+                                                c_void_p(out.data_ptr()), _stream()))
+        return out
+
+    def model_forward(self, x, t, uncond, style_eps):
+        B = x.shape[0]
+        x = _f32(x, self.device)
+        t = t.to(self.device).long().contiguous()
+        eps = _f32(style_eps, self.device)
+        out = torch.empty(B, self.dims.njoints, self.dims.nfeats, 34, dtype=torch.float32, device=self.device)
+        mu = torch.empty(B, 1, self.dims.latent_dim, dtype=torch.float32, device=self.device)
+        lv = torch.empty_like(mu)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_model_forward(self.h, B, c_void_p(x.data_ptr()), c_void_p(t.data_ptr()),
+                                                  1 if uncond else 0, c_void_p(eps.data_ptr()),
+                                                  c_void_p(out.data_ptr()), c_void_p(mu.data_ptr()),
+                                                  c_void_p(lv.data_ptr()), _stream()))
+        return out, mu, lv
+
+    def cfg_forward(self, x, t, eps_c, eps_u, scale):
+        B = x.shape[0]
+        x = _f32(x, self.device)
+        t = t.to(self.device).long().contiguous()
+        eps_c, eps_u, scale = _f32(eps_c, self.device), _f32(eps_u, self.device), _f32(scale, self.device)
+        out = torch.empty(B, self.dims.njoints, self.dims.nfeats, 34, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_cfg_forward(self.h, B, c_void_p(x.data_ptr()), c_void_p(t.data_ptr()),
+                                                c_void_p(eps_c.data_ptr()), c_void_p(eps_u.data_ptr()),
+                                                c_void_p(scale.data_ptr()), c_void_p(out.data_ptr()), _stream()))
+        return out
+
+    def step(self, params, x_t, eps_c, eps_u, noise, scale, x_prev, pred_x0):
+        """One fused denoising step.  x_t / x_prev / pred_x0: dense fp32 [B,J,D,F] on the
+        device; noise: any [B,J,D,F] tensor whose (J,D) dims collapse, else it is copied."""
+        B = x_t.shape[0]
+        nb = nj = nf = 0
+        nptr = None
+        if noise is not None:
+            sb, sj, sd, sf = noise.stride()
+            if noise.dtype != torch.float32 or noise.device != self.device or sj != sd * noise.shape[2]:
+                noise = _f32(noise, self.device)
+                sb, sj, sd, sf = noise.stride()
+            nb, nj, nf, nptr = sb, sd, sf, c_void_p(noise.data_ptr())
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_step(self.h, B, byref(params), c_void_p(x_t.data_ptr()),
+                                         c_void_p(eps_c.data_ptr()), c_void_p(eps_u.data_ptr()), nptr, nb, nj, nf,
+                                         c_void_p(scale.data_ptr()),
+                                         c_void_p(x_prev.data_ptr()) if x_prev is not None else None,
+                                         c_void_p(pred_x0.data_ptr()) if pred_x0 is not None else None, _stream()))
+
+    def q_sample(self, x0, noise, c_x0, c_noise):
+        x0 = _f32(x0, self.device)
+        noise = _f32(noise, self.device)
+        out = torch.empty_like(x0)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_q_sample(self.h, x0.numel(), c_void_p(x0.data_ptr()), c_void_p(noise.data_ptr()),
+                                             float(c_x0), float(c_noise), c_void_p(out.data_ptr()), _stream()))
+        return out

@@ -1,0 +1,453 @@
+"""Diffusion process + samplers with the reference's Python surface.
+
+Mirrors scripts/diffusion/gaussian_diffusion.py (names, signatures, return values,
+attribute tables) for the SAMPLING path: schedules (:26-70), derived fp64 tables
+(:167-204), q_sample (:240-258), q_posterior_mean_variance (:260-282),
+p_mean_variance (:284-399), p_sample (:507-558), p_sample_loop[_progressive]
+(:608-743), ddim_sample (:745-798), ddim_sample_loop[_progressive] (:895-1014),
+condition_mean / condition_score (:429-481), _extract_into_tensor (:1651-1664).
+Training losses, VLB terms, PLMS and the *_with_grad samplers are outside the
+hot path and raise NotImplementedError.
+
+Two execution routes:
+  * fused  - the model is this package's ClassifierFreeSampleModel(RAG) and no Python
+    hook (cond_fn / denoised_fn / inpainting) is active: each step is ONE C-ABI call
+    (`ls_step`: both denoiser passes + guidance + sampler update).  This is what the
+    shipped eval scripts exercise.
+  * generic - anything else: the model is called like in the reference and the
+    sampler arithmetic uses torch elementwise ops on the device.
+
+Random draws are made with torch in exactly the reference's order AND memory layout
+(see `_LikeLayouts`), so the same seed on the same device yields the same numbers.
+"""
+import enum
+import math
+from copy import deepcopy
+
+import numpy as np
+import torch as th
+
+from ._cabi import LsStepParams
+
+
+def get_named_beta_schedule(schedule_name, num_diffusion_timesteps, scale_betas=1.):
+    if schedule_name == "linear":
+        scale = scale_betas * 1000 / num_diffusion_timesteps
+        return np.linspace(scale * 0.0001, scale * 0.02, num_diffusion_timesteps, dtype=np.float64)
+    if schedule_name == "cosine":
+        return betas_for_alpha_bar(num_diffusion_timesteps,
+                                   lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2)
+    raise NotImplementedError("unknown beta schedule: %s" % schedule_name)
+
+
+def betas_for_alpha_bar(num_diffusion_timesteps, alpha_bar, max_beta=0.999):
+    n = num_diffusion_timesteps
+    return np.array([min(1 - alpha_bar((i + 1) / n) / alpha_bar(i / n), max_beta) for i in range(n)])
+
+
+class ModelMeanType(enum.Enum):
+    PREVIOUS_X = enum.auto()
+    START_X = enum.auto()
+    EPSILON = enum.auto()
+
+
+class ModelVarType(enum.Enum):
+    LEARNED = enum.auto()
+    FIXED_SMALL = enum.auto()
+    FIXED_LARGE = enum.auto()
+    LEARNED_RANGE = enum.auto()
+
+
+class LossType(enum.Enum):
+    MSE = enum.auto()
+    RESCALED_MSE = enum.auto()
+    KL = enum.auto()
+    RESCALED_KL = enum.auto()
+    HUBER = enum.auto()
+
+    def is_vb(self):
+        return self in (LossType.KL, LossType.RESCALED_KL)
+
+
+class TorchNoise:
+    """Default noise source: torch's generator on the sampling device."""
+
+    def randn(self, shape, device):
+        return th.randn(*shape, device=device)
+
+    def randn_like(self, like):
+        return th.randn_like(like)
+
+
+class ReplayNoise:
+    """Replays a recorded list of draws (tests feed the oracle's NoiseTape through this)."""
+
+    def __init__(self, draws):
+        self.draws, self.pos = list(draws), 0
+
+    def _next(self, shape, device):
+        t = self.draws[self.pos]
+        self.pos += 1
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), tuple(shape))
+        return t.to(device)
+
+    def randn(self, shape, device):
+        return self._next(shape, device)
+
+    def randn_like(self, like):
+        return self._next(like.shape, like.device)
+
+
+def _extract_into_tensor(arr, timesteps, broadcast_shape):
+    """fp64 table -> fp32 values gathered at `timesteps`, broadcast to `broadcast_shape`."""
+    res = th.from_numpy(arr).to(device=timesteps.device)[timesteps].float()
+    while len(res.shape) < len(broadcast_shape):
+        res = res[..., None]
+    return res.expand(broadcast_shape)
+
+
+class GaussianDiffusion:
+    def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False,
+                 lambda_rcxyz=0., lambda_vel=0., lambda_pose=1., lambda_orient=1., lambda_loc=1.,
+                 data_rep='rot6d', lambda_root_vel=0., lambda_vel_rcxyz=0., lambda_fc=0.):
+        self.model_mean_type, self.model_var_type, self.loss_type = model_mean_type, model_var_type, loss_type
+        self.rescale_timesteps, self.data_rep = rescale_timesteps, data_rep
+        if data_rep != 'rot_vel' and lambda_pose != 1.:
+            raise ValueError('lambda_pose is relevant only when training on velocities!')
+        self.lambda_pose, self.lambda_orient, self.lambda_loc = lambda_pose, lambda_orient, lambda_loc
+        self.lambda_rcxyz, self.lambda_vel, self.lambda_root_vel = lambda_rcxyz, lambda_vel, lambda_root_vel
+        self.lambda_vel_rcxyz, self.lambda_fc = lambda_vel_rcxyz, lambda_fc
+
+        betas = np.array(betas, dtype=np.float64)
+        assert betas.ndim == 1, "betas must be 1-D"
+        assert (betas > 0).all() and (betas <= 1).all()
+        self.betas = betas
+        self.num_timesteps = int(betas.shape[0])
+        alphas = 1.0 - betas
+        ac = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod = ac
+        self.alphas_cumprod_prev = np.append(1.0, ac[:-1])
+        self.alphas_cumprod_next = np.append(ac[1:], 0.0)
+        self.sqrt_alphas_cumprod = np.sqrt(ac)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - ac)
+        self.log_one_minus_alphas_cumprod = np.log(1.0 - ac)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / ac)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / ac - 1)
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - ac)
+        self.posterior_log_variance_clipped = np.log(
+            np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - ac)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - ac)
+
+        self.noise_source = TorchNoise()
+        # 'pred_xstart' is what p_sample_loop(dump_steps=...) collects in the TED tree
+        # (gaussian_diffusion.py:667); the BEAT twin collects 'sample' (scripts_beat/...:665).
+        self.dump_key = "pred_xstart"
+        self.allow_ddim_const_noise = True   # BEAT twin raises instead (scripts_beat/...:913-914)
+
+    # ------------------------------------------------------------------ forward process
+    def q_mean_variance(self, x_start, t):
+        mean = _extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+        variance = _extract_into_tensor(1.0 - self.alphas_cumprod, t, x_start.shape)
+        log_variance = _extract_into_tensor(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+        return mean, variance, log_variance
+
+    def q_sample(self, x_start, t, noise=None):
+        if noise is None:
+            noise = self.noise_source.randn_like(x_start)
+        assert noise.shape == x_start.shape
+        return (_extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+                + _extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+
+    def q_posterior_mean_variance(self, x_start, x_t, t):
+        assert x_start.shape == x_t.shape
+        mean = (_extract_into_tensor(self.posterior_mean_coef1, t, x_t.shape) * x_start
+                + _extract_into_tensor(self.posterior_mean_coef2, t, x_t.shape) * x_t)
+        var = _extract_into_tensor(self.posterior_variance, t, x_t.shape)
+        log_var = _extract_into_tensor(self.posterior_log_variance_clipped, t, x_t.shape)
+        return mean, var, log_var
+
+    # ------------------------------------------------------------------ generic route
+    def _fixed_variance_tables(self):
+        if self.model_var_type == ModelVarType.FIXED_LARGE:
+            v = np.append(self.posterior_variance[1], self.betas[1:])
+            return v, np.log(v)
+        if self.model_var_type == ModelVarType.FIXED_SMALL:
+            return self.posterior_variance, self.posterior_log_variance_clipped
+        raise NotImplementedError("learned variances are not used by LivelySpeaker (model_util.py:42-74)")
+
+    def p_mean_variance(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None):
+        if model_kwargs is None:
+            model_kwargs = {}
+        B = x.shape[0]
+        assert t.shape == (B,)
+        model_output = model(x, self._scale_timesteps(t), **model_kwargs)
+        y = model_kwargs.get('y', {})
+        if 'inpainting_mask' in y and 'inpainted_motion' in y:
+            mask, motion = y['inpainting_mask'], y['inpainted_motion']
+            assert self.model_mean_type == ModelMeanType.START_X
+            assert model_output.shape == mask.shape == motion.shape
+            if getattr(self, "inpaint_noised", True):     # TED tree: gaussian_diffusion.py:319-320
+                motion = self.q_sample(motion, t - 1) if (t[0] > 0) else motion
+            model_output = (model_output * ~mask) + (motion * mask)
+        var_tab, logvar_tab = self._fixed_variance_tables()
+        model_variance = _extract_into_tensor(var_tab, t, x.shape)
+        model_log_variance = _extract_into_tensor(logvar_tab, t, x.shape)
+
+        def finish(v):
+            if denoised_fn is not None:
+                v = denoised_fn(v)
+            return v.clamp(-1, 1) if clip_denoised else v
+
+        if self.model_mean_type == ModelMeanType.START_X:
+            pred_xstart = finish(model_output)
+        elif self.model_mean_type == ModelMeanType.EPSILON:
+            pred_xstart = finish(self._predict_xstart_from_eps(x_t=x, t=t, eps=model_output))
+        else:
+            raise NotImplementedError(self.model_mean_type)
+        model_mean, _, _ = self.q_posterior_mean_variance(x_start=pred_xstart, x_t=x, t=t)
+        assert model_mean.shape == model_log_variance.shape == pred_xstart.shape == x.shape
+        return {"mean": model_mean, "variance": model_variance, "log_variance": model_log_variance,
+                "pred_xstart": pred_xstart}
+
+    def _predict_xstart_from_eps(self, x_t, t, eps):
+        assert x_t.shape == eps.shape
+        return (_extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t
+                - _extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * eps)
+
+    def _predict_eps_from_xstart(self, x_t, t, pred_xstart):
+        return ((_extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t - pred_xstart)
+                / _extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape))
+
+    def _scale_timesteps(self, t):
+        if self.rescale_timesteps:
+            return t.float() * (1000.0 / self.num_timesteps)
+        return t
+
+    def condition_mean(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        gradient = cond_fn(x, self._scale_timesteps(t), **model_kwargs)
+        return p_mean_var["mean"].float() + p_mean_var["variance"] * gradient.float()
+
+    def condition_score(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
+        eps = self._predict_eps_from_xstart(x, t, p_mean_var["pred_xstart"])
+        eps = eps - (1 - alpha_bar).sqrt() * cond_fn(x, self._scale_timesteps(t), **model_kwargs)
+        out = p_mean_var.copy()
+        out["pred_xstart"] = self._predict_xstart_from_eps(x, t, eps)
+        out["mean"], _, _ = self.q_posterior_mean_variance(x_start=out["pred_xstart"], x_t=x, t=t)
+        return out
+
+    def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                 const_noise=False):
+        out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                   model_kwargs=model_kwargs)
+        noise = self.noise_source.randn_like(x)
+        if const_noise:
+            noise = noise[[0]].repeat(x.shape[0], 1, 1, 1)
+        nonzero_mask = (t != 0).float().view(-1, *([1] * (len(x.shape) - 1)))
+        if cond_fn is not None:
+            out["mean"] = self.condition_mean(cond_fn, out, x, t, model_kwargs=model_kwargs)
+        sample = out["mean"] + nonzero_mask * th.exp(0.5 * out["log_variance"]) * noise
+        return {"sample": sample, "pred_xstart": out["pred_xstart"]}
+
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                    eta=0.0, const_noise=False):
+        out_orig = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                        model_kwargs=model_kwargs)
+        out = out_orig if cond_fn is None else self.condition_score(cond_fn, out_orig, x, t,
+                                                                    model_kwargs=model_kwargs)
+        eps = self._predict_eps_from_xstart(x, t, out["pred_xstart"])
+        alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
+        alpha_bar_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, x.shape)
+        sigma = eta * th.sqrt((1 - alpha_bar_prev) / (1 - alpha_bar)) * th.sqrt(1 - alpha_bar / alpha_bar_prev)
+        noise = self.noise_source.randn_like(x)
+        if const_noise:
+            noise = noise[[0]].repeat(noise.shape[0], 1, 1, 1)
+        mean_pred = out["pred_xstart"] * th.sqrt(alpha_bar_prev) + th.sqrt(1 - alpha_bar_prev - sigma ** 2) * eps
+        nonzero_mask = (t != 0).float().view(-1, *([1] * (len(x.shape) - 1)))
+        return {"sample": mean_pred + nonzero_mask * sigma * noise, "pred_xstart": out_orig["pred_xstart"]}
+
+    # ------------------------------------------------------------------ fused route
+    def _model_timestep(self, i):
+        """Spaced index -> the timestep the denoiser sees (identity for an unspaced process)."""
+        return int(i)
+
+    def step_params(self, i, ddim=False, eta=0.0, clip_denoised=True):
+        """ls_step_params for spaced index i.  fp64 table entries are cast to fp32 exactly
+        where _extract_into_tensor casts them; DDIM's sigma / sqrt terms are then computed
+        in fp32 like th.sqrt on the gathered tensors (gaussian_diffusion.py:779-792)."""
+        f32 = np.float32
+        p = LsStepParams()
+        p.t_model = self._model_timestep(i)
+        p.clip_denoised = 1 if clip_denoised else 0
+        p.add_noise = 1 if i != 0 else 0
+        if not ddim:
+            p.mode = 0
+            c = [f32(self.posterior_mean_coef1[i]), f32(self.posterior_mean_coef2[i]),
+                 f32(self.posterior_log_variance_clipped[i])]
+        else:
+            p.mode = 1
+            ab, ab_prev = f32(self.alphas_cumprod[i]), f32(self.alphas_cumprod_prev[i])
+            one = f32(1)
+            sigma = f32(eta) * np.sqrt((one - ab_prev) / (one - ab)) * np.sqrt(one - ab / ab_prev)
+            sigma = f32(sigma)
+            c = [f32(self.sqrt_recip_alphas_cumprod[i]), f32(self.sqrt_recipm1_alphas_cumprod[i]),
+                 np.sqrt(ab_prev), np.sqrt(f32(one - ab_prev - f32(sigma * sigma))), sigma]
+        for k, v in enumerate(c):
+            p.c[k] = float(v)
+        return p
+
+    def _fusable(self, model, denoised_fn, cond_fn, cond_fn_with_grad, randomize_class, model_kwargs):
+        from .cfg_sampler import ClassifierFreeSampleModel
+        from .rag import RAG
+        if not (isinstance(model, ClassifierFreeSampleModel) and isinstance(model.model, RAG)):
+            return False
+        if denoised_fn is not None or cond_fn is not None or cond_fn_with_grad or randomize_class:
+            return False
+        if self.model_mean_type != ModelMeanType.START_X or self.rescale_timesteps:
+            return False
+        if self.model_var_type != ModelVarType.FIXED_SMALL:
+            return False
+        y = (model_kwargs or {}).get('y', {})
+        if 'inpainting_mask' in y and 'inpainted_motion' in y:
+            return False
+        return model.model.cond_mask_prob > 0 and not model.model.training
+
+    def _sample_loop_progressive(self, ddim, model, shape, noise, clip_denoised, denoised_fn, cond_fn,
+                                 model_kwargs, device, progress, eta, skip_timesteps, init_image,
+                                 randomize_class, cond_fn_with_grad, const_noise):
+        if cond_fn_with_grad:
+            raise NotImplementedError("*_with_grad samplers are outside the sampling hot path (SURVEY.md 8f)")
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        src = self.noise_source
+        if noise is not None:
+            img = noise
+        else:
+            img = src.randn(tuple(shape), device)
+            if const_noise:
+                img = img[[0]].repeat(img.shape[0], 1, 1, 1)
+        if skip_timesteps and init_image is None:
+            init_image = th.zeros_like(img)
+        indices = list(range(self.num_timesteps - skip_timesteps))[::-1]
+        fused = self._fusable(model, denoised_fn, cond_fn, cond_fn_with_grad, randomize_class, model_kwargs)
+
+        if not fused:
+            if init_image is not None:
+                my_t = th.ones([shape[0]], device=device, dtype=th.long) * indices[0]
+                img = self.q_sample(init_image, my_t, img)
+            if progress:
+                from tqdm.auto import tqdm
+                indices = tqdm(indices)
+            for i in indices:
+                t = th.tensor([i] * shape[0], device=device)
+                if randomize_class and 'y' in model_kwargs:
+                    model_kwargs['y'] = th.randint(low=0, high=model.num_classes, size=model_kwargs['y'].shape,
+                                                   device=model_kwargs['y'].device)
+                with th.no_grad():
+                    if ddim:
+                        out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                               cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta,
+                                               const_noise=const_noise)
+                    else:
+                        out = self.p_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                            cond_fn=cond_fn, model_kwargs=model_kwargs, const_noise=const_noise)
+                    yield out
+                    img = out["sample"]
+            return
+
+        # ---- fused route -------------------------------------------------------------
+        rag = model.model
+        y = model_kwargs['y']
+        B = int(shape[0])
+        eng = rag.engine(B)
+        dev = eng.device
+        with th.no_grad():
+            eng.set_cond(y, force=True)
+            scale = y['scale'].to(dev, non_blocking=True).float().contiguous()
+            # `like` carries the strides the reference's randn_like(x) would see: x_T's own
+            # for the first executed step, the [F,B,J,D] memory order afterwards.
+            like = img if init_image is None else init_image
+            if init_image is not None:
+                i0 = indices[0]
+                img = eng.q_sample(init_image, img, np.float32(self.sqrt_alphas_cumprod[i0]),
+                                   np.float32(self.sqrt_one_minus_alphas_cumprod[i0]))
+            x_cur = img.to(dev).float().contiguous()
+            if like.device != dev:
+                like = x_cur
+            perm_like = th.empty(shape[3], B, shape[1], shape[2], device=dev).permute(1, 2, 3, 0)
+            if progress:
+                from tqdm.auto import tqdm
+                indices = tqdm(indices)
+            for k, i in enumerate(indices):
+                eps_c = src.randn((B, 1, rag.latent_dim), dev)
+                eps_u = src.randn((B, 1, rag.latent_dim), dev)
+                nz = src.randn_like(like if k == 0 else perm_like)
+                if const_noise:
+                    nz = nz[[0]].expand(B, -1, -1, -1)
+                x_next = th.empty_like(x_cur)
+                x0 = th.empty_like(x_cur)
+                eng.step(self.step_params(i, ddim=ddim, eta=eta, clip_denoised=clip_denoised), x_cur, eps_c, eps_u,
+                         nz, scale, x_next, x0)
+                yield {"sample": x_next, "pred_xstart": x0}
+                x_cur = x_next
+
+    # ------------------------------------------------------------------ public loops
+    def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                      model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                      randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False):
+        final, dump = None, []
+        for i, sample in enumerate(self.p_sample_loop_progressive(
+                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                model_kwargs=model_kwargs, device=device, progress=progress, skip_timesteps=skip_timesteps,
+                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad,
+                const_noise=const_noise)):
+            if dump_steps is not None and i in dump_steps:
+                dump.append(deepcopy(sample[self.dump_key]))
+            final = sample
+        if dump_steps is not None:
+            return dump
+        return final["sample"]
+
+    def p_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                  cond_fn=None, model_kwargs=None, device=None, progress=False, skip_timesteps=0,
+                                  init_image=None, randomize_class=False, cond_fn_with_grad=False,
+                                  const_noise=False):
+        return self._sample_loop_progressive(False, model, shape, noise, clip_denoised, denoised_fn, cond_fn,
+                                             model_kwargs, device, progress, 0.0, skip_timesteps, init_image,
+                                             randomize_class, cond_fn_with_grad, const_noise)
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0,
+                         init_image=None, randomize_class=False, cond_fn_with_grad=False, dump_steps=None,
+                         const_noise=False):
+        if dump_steps is not None:
+            raise NotImplementedError()
+        if const_noise and not self.allow_ddim_const_noise:
+            raise NotImplementedError()
+        final = None
+        for sample in self.ddim_sample_loop_progressive(
+                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                model_kwargs=model_kwargs, device=device, progress=progress, eta=eta,
+                skip_timesteps=skip_timesteps, init_image=init_image, randomize_class=randomize_class,
+                cond_fn_with_grad=cond_fn_with_grad, const_noise=const_noise):
+            final = sample
+        return final["sample"]
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                     cond_fn=None, model_kwargs=None, device=None, progress=False, eta=0.0,
+                                     skip_timesteps=0, init_image=None, randomize_class=False,
+                                     cond_fn_with_grad=False, const_noise=False):
+        return self._sample_loop_progressive(True, model, shape, noise, clip_denoised, denoised_fn, cond_fn,
+                                             model_kwargs, device, progress, eta, skip_timesteps, init_image,
+                                             randomize_class, cond_fn_with_grad, const_noise)
+
+    # ------------------------------------------------------------------ out of scope
+    def _out_of_scope(self, *a, **k):
+        raise NotImplementedError("training / VLB / PLMS / *_with_grad are outside the sampling hot path "
+                                  "(SURVEY.md section 8f)")
+
+    training_losses = plms_sample = plms_sample_loop = plms_sample_loop_progressive = _out_of_scope
+    p_sample_with_grad = ddim_sample_with_grad = ddim_reverse_sample = _out_of_scope
+    calc_bpd_loop = _vb_terms_bpd = _prior_bpd = _out_of_scope

@@ -1,0 +1,130 @@
+"""Oracle (test infrastructure): ancestral / DDIM sampling loops.
+
+torch-CPU fp32 restatement of the reference's sampling loop with the random
+draws made explicit.  ``NoiseTape`` performs the draws in the reference's
+order and records them so the CUDA path can replay the
+identical numbers.
+
+Reference:
+  scripts/diffusion/gaussian_diffusion.py:240-258    q_sample
+  scripts/diffusion/gaussian_diffusion.py:260-282    q_posterior_mean_variance
+  scripts/diffusion/gaussian_diffusion.py:284-399    p_mean_variance (START_X, FIXED_SMALL)
+  scripts/diffusion/gaussian_diffusion.py:507-558    p_sample
+  scripts/diffusion/gaussian_diffusion.py:673-743    p_sample_loop_progressive
+  scripts/diffusion/gaussian_diffusion.py:745-798    ddim_sample
+  scripts/diffusion/gaussian_diffusion.py:945-1014   ddim_sample_loop_progressive
+  scripts/diffusion/gaussian_diffusion.py:1651-1664  _extract_into_tensor (fp64 -> fp32 cast)
+  scripts/diffusion/respace.py:118-130               _WrappedModel (spaced t -> original t)
+"""
+import numpy as np
+import torch
+
+from . import rag_oracle
+
+
+class NoiseTape:
+    """Draws N(0,1) tensors from a torch generator in call order and keeps them."""
+
+    def __init__(self, seed=None, device="cpu", replay=None):
+        self.replay = list(replay) if replay is not None else None
+        self.record = []
+        self.gen = None
+        self.device = device
+        if self.replay is None:
+            self.gen = torch.Generator(device=device)
+            self.gen.manual_seed(seed)
+
+    def draw(self, *shape):
+        """th.randn(*shape): a fresh contiguous tensor."""
+        if self.replay is not None:
+            t = self.replay[len(self.record)]
+            assert tuple(t.shape) == tuple(shape), (t.shape, shape)
+        else:
+            t = torch.randn(*shape, generator=self.gen, device=self.device)
+        self.record.append(t)
+        return t
+
+    def draw_like(self, x):
+        """th.randn_like(x): same STRIDES as x.  This matters: from the second step on
+        x_t is a dense but permuted tensor (memory order [F,B,J,D], inherited from
+        OutputProcess' permute, RAG.py:209-210), and torch fills such a tensor in
+        memory order - on CPU through a different code path that also consumes the
+        generator differently.  Drawing on an empty_like(x) reproduces both effects."""
+        if self.replay is not None:
+            t = self.replay[len(self.record)]
+            assert tuple(t.shape) == tuple(x.shape), (t.shape, x.shape)
+        else:
+            t = torch.empty_like(x).normal_(generator=self.gen)
+        self.record.append(t)
+        return t
+
+
+def _pick(table, i):
+    """_extract_into_tensor for a batch-uniform index: fp64 entry -> fp32 scalar tensor."""
+    return torch.from_numpy(np.asarray(table))[i].float()
+
+
+def q_sample(tab, x0, i, noise):
+    return _pick(tab["sqrt_alphas_cumprod"], i) * x0 + _pick(tab["sqrt_one_minus_alphas_cumprod"], i) * noise
+
+
+def _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised):
+    B = x.shape[0]
+    t_orig = torch.full((B,), tmap[i], dtype=torch.long)
+    e_c = tape.draw(B, 1, sd["speaker_mu.weight"].shape[0])
+    e_u = tape.draw(B, 1, sd["speaker_mu.weight"].shape[0])
+    x0 = rag_oracle.cfg_forward(sd, x, t_orig, y, e_c, e_u, nj, nf)
+    if clip_denoised:
+        x0 = x0.clamp(-1, 1)
+    return x0
+
+
+def p_sample_step(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised=False, const_noise=False):
+    """One ancestral step.  Returns (sample, pred_xstart)."""
+    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised)
+    mean = _pick(tab["posterior_mean_coef1"], i) * x0 + _pick(tab["posterior_mean_coef2"], i) * x
+    log_var = _pick(tab["posterior_log_variance_clipped"], i)
+    noise = tape.draw_like(x)      # gaussian_diffusion.py:543 / :787 randn_like(x)
+    if const_noise:
+        noise = noise[[0]].repeat(x.shape[0], 1, 1, 1)
+    nz = 0.0 if i == 0 else 1.0
+    return mean + nz * torch.exp(0.5 * log_var) * noise, x0
+
+
+def ddim_step(sd, tab, tmap, x, i, y, tape, nj, nf, eta=0.0, clip_denoised=False, const_noise=False):
+    """One DDIM step.  Returns (sample, pred_xstart)."""
+    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised)
+    eps = (_pick(tab["sqrt_recip_alphas_cumprod"], i) * x - x0) / _pick(tab["sqrt_recipm1_alphas_cumprod"], i)
+    ab = _pick(tab["alphas_cumprod"], i)
+    ab_prev = _pick(tab["alphas_cumprod_prev"], i)
+    sigma = eta * torch.sqrt((1 - ab_prev) / (1 - ab)) * torch.sqrt(1 - ab / ab_prev)
+    noise = tape.draw_like(x)      # gaussian_diffusion.py:543 / :787 randn_like(x)
+    if const_noise:
+        noise = noise[[0]].repeat(x.shape[0], 1, 1, 1)
+    mean = x0 * torch.sqrt(ab_prev) + torch.sqrt(1 - ab_prev - sigma ** 2) * eps
+    nz = 0.0 if i == 0 else 1.0
+    return mean + nz * sigma * noise, x0
+
+
+def sample_loop(sd, tab, tmap, shape, y, tape, ddim=False, eta=0.0, clip_denoised=False,
+                skip_timesteps=0, init_image=None, const_noise=False, noise=None, trace=None):
+    """p_sample_loop / ddim_sample_loop.  ``trace`` (a list) receives
+    (i, sample, pred_xstart) per step when given."""
+    B, nj, nf, _ = shape
+    n_t = len(tab["betas"])
+    img = noise if noise is not None else tape.draw(*shape)
+    if noise is None and const_noise:
+        img = img[[0]].repeat(B, 1, 1, 1)
+    if skip_timesteps and init_image is None:
+        init_image = torch.zeros_like(img)
+    indices = list(range(n_t - skip_timesteps))[::-1]
+    if init_image is not None:
+        img = q_sample(tab, init_image, indices[0], img)
+    step = ddim_step if ddim else p_sample_step
+    for i in indices:
+        kw = {"eta": eta} if ddim else {}
+        img, x0 = step(sd, tab, tmap, img, i, y, tape, nj, nf, clip_denoised=clip_denoised,
+                       const_noise=const_noise, **kw)
+        if trace is not None:
+            trace.append((i, img, x0))
+    return img

@@ -1,0 +1,323 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle
+on the same seeded inputs / recorded noise and against the committed reference fixtures.
+Tolerance = BASELINE.json north_star: rtol 1e-3, atol 1e-4 (fp32)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import livelyspeaker_b200 as ls
+from conftest import ATOL, RTOL
+from livelyspeaker_b200 import beat_model_util, synthetic
+from oracle import rag_oracle, sampler_oracle, schedule_oracle
+from test_oracle_golden import LOOPS, run_oracle_loop
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _args(**kw):
+    a = dict(mdm_condm='text', latent_dim=512, ff_size=1024, layers=8, cond_mask_prob=0.1, arch='trans_enc',
+             emb_trans_dec=False, dataset='humanml', lang_model=None, mlpact='silu', diffusion_steps=1000,
+             noise_schedule='cosine', sigma_small=True, lambda_vel=1.0, lambda_rcxyz=0.0, lambda_fc=0.0)
+    a.update(kw)
+    return types.SimpleNamespace(**a)
+
+
+def _close(got, want, rtol=RTOL, atol=ATOL):
+    got = got.detach().cpu().numpy() if torch.is_tensor(got) else np.asarray(got)
+    want = want.detach().cpu().numpy() if torch.is_tensor(want) else np.asarray(want)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def build(name, respacing, steps=1000, impl="auto"):
+    dims = synthetic.dims_for(name)
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    if name == "ted":
+        model, diffusion = ls.create_model_and_diffusion(_args(diffusion_steps=steps), respacing)
+    else:
+        model, diffusion = beat_model_util.create_model_and_diffusion(_args(diffusion_steps=steps, njoints=47),
+                                                                      respacing)
+    ls.load_model_wo_clip(model, sd)
+    model.set_impl(impl)
+    cfg = ls.ClassifierFreeSampleModel(model).to(DEV).eval()
+    return dims, sd, cfg, diffusion
+
+
+IMPLS = ["simt", "auto"]
+
+
+def test_wav_encoder(golden_ted):
+    dims, sd, cfg, _ = build("ted", "ddim100")
+    y = synthetic.synth_cond(dims, 2)
+    got = cfg.model.engine(2).wav_encoder(y["audio_input"].to(DEV))
+    _close(got, golden_ted["wavenc_out"])
+    # ragged batch (not a multiple of the internal chunk) and B=1
+    y = synthetic.synth_cond(dims, 67, seed=9)
+    got = cfg.model.engine(67).wav_encoder(y["audio_input"].to(DEV))
+    with torch.no_grad():
+        want = rag_oracle.wav_encoder(sd, y["audio_input"])
+    _close(got, want)
+
+
+def test_precompute_buffers_and_origin_side_effect():
+    dims, sd, cfg, _ = build("ted", "ddim100")
+    y = synthetic.synth_cond(dims, 3, device=DEV)
+    assert float(y["origin_x"][..., 4:].abs().max()) > 0
+    eng = cfg.model.engine(3)
+    eng.set_cond(y)
+    torch.cuda.synchronize()
+    assert float(y["origin_x"][..., 4:].abs().max()) == 0.0          # RAG.py:110 side effect
+    yc = synthetic.synth_cond(dims, 3)
+    W = sd["input_mapping.weight"]
+    with torch.no_grad():
+        af = rag_oracle.wav_encoder(sd, yc["audio_input"])
+        A = af @ W[:, 2 * 27 + 1:].T
+        ox = yc["origin_x"].clone()
+        ox[..., 4:] = 0
+        oxf = ox.permute(0, 3, 1, 2).reshape(3, 34, 27)
+        bit = torch.zeros(3, 34, 1)
+        bit[:, :4] = 1
+        P = oxf @ W[:, 27:54].T + bit * W[:, 54] + sd["input_mapping.bias"]
+        z = sd["speaker_embedding.weight"][yc["vid_indices"]]
+        mu = z @ sd["speaker_mu.weight"].T + sd["speaker_mu.bias"]
+        lv = z @ sd["speaker_logvar.weight"].T + sd["speaker_logvar.bias"]
+    _close(eng.debug_buffer(0).view(3, 34, 512), A)
+    _close(eng.debug_buffer(1).view(3, 34, 512), P)
+    _close(eng.debug_buffer(2).view(3, 512), mu)
+    _close(eng.debug_buffer(3).view(3, 512), lv)
+    tt = torch.tensor([0, 17, 990, 999])
+    with torch.no_grad():
+        want = rag_oracle.timestep_embed(sd, tt)
+    _close(eng.debug_buffer(4).view(1000, 512)[tt.to(DEV)], want)
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_rag_forward_and_cfg_vs_reference_fixtures(name, golden_ted, golden_beat):
+    g = golden_ted if name == "ted" else golden_beat
+    dims, sd, cfg, _ = build(name, "ddim100")
+    x, t = torch.from_numpy(g["fwd_x"]).to(DEV), torch.from_numpy(g["fwd_t"]).to(DEV)
+    eng = cfg.model.engine(2)
+    eps = torch.randn(2, 1, 512, generator=torch.Generator().manual_seed(11)).to(DEV)
+    for tag, unc in (("cond", False), ("uncond", True)):
+        y = synthetic.synth_cond(dims, 2, device=DEV)
+        eng.set_cond(y)
+        out, mu, lv = eng.model_forward(x, t, unc, eps)
+        _close(out, g["fwd_%s_output" % tag])
+        _close(mu, g["fwd_%s_z_mu" % tag])
+        _close(lv, g["fwd_%s_z_logvar" % tag])
+    tape = sampler_oracle.NoiseTape(seed=12)
+    e_c, e_u = tape.draw(2, 1, 512).to(DEV), tape.draw(2, 1, 512).to(DEV)
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    eng.set_cond(y)
+    _close(eng.cfg_forward(x, t, e_c, e_u, y["scale"]), g["cfg_out"])
+    # module-level call: same contract as the reference's RAG.forward
+    r = cfg.model(x, t, synthetic.synth_cond(dims, 2, device=DEV))
+    assert set(r) == {"output", "z_mu", "z_logvar"} and r["output"].shape == x.shape
+    assert r["z_mu"].shape == (2, 1, 512)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_single_steps_vs_reference_fixtures(name, impl, golden_ted, golden_beat):
+    g = golden_ted if name == "ted" else golden_beat
+    dims = synthetic.dims_for(name)
+    xs = torch.from_numpy(g["step_x"])
+    for ddim, cases in ((False, [(999, 0.0), (500, 0.0), (1, 0.0), (0, 0.0)]),
+                        (True, [(99, 0.0), (57, 0.0), (57, 0.5), (0, 0.0)])):
+        dims, sd, cfg, diffusion = build(name, "ddim100" if ddim else "", impl=impl)
+        tab, tmap = schedule_oracle.build("cosine", 1000, "ddim100" if ddim else "")
+        eng = cfg.model.engine(2)
+        for i, eta in cases:
+            seed = (200 if ddim else 100) + i
+            tape = sampler_oracle.NoiseTape(seed=seed)
+            fn = sampler_oracle.ddim_step if ddim else sampler_oracle.p_sample_step
+            with torch.no_grad():
+                fn(sd, tab, tmap, xs, i, synthetic.synth_cond(dims, 2), tape, dims.njoints, dims.nfeats,
+                   **({"eta": eta} if ddim else {}))
+            e_c, e_u, nz = [t.to(DEV) for t in tape.record]
+            y = synthetic.synth_cond(dims, 2, device=DEV)
+            eng.set_cond(y, force=True)
+            x_t = xs.to(DEV)
+            x_prev, x0 = torch.empty_like(x_t), torch.empty_like(x_t)
+            eng.step(diffusion.step_params(i, ddim=ddim, eta=eta, clip_denoised=False), x_t, e_c, e_u, nz, y["scale"],
+                     x_prev, x0)
+            tag = ("dstep%d_eta%d" % (i, int(eta * 10))) if ddim else ("pstep%d" % i)
+            _close(x_prev, g[tag + "_sample"])
+            _close(x0, g[tag + "_x0"])
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("tag", list(LOOPS))
+def test_whole_loops_ted(tag, impl, golden_ted):
+    spec, steps, ddim, seed, B, kw = LOOPS[tag]
+    dims, sd, cfg, diffusion = build("ted", spec, steps, impl=impl)
+    want, tape = run_oracle_loop(tag, golden_ted, dims, sd)
+    diffusion.noise_source = ls.ReplayNoise(tape.record)
+    kw = dict(kw)
+    init = torch.from_numpy(golden_ted["init_image"]).to(DEV) if kw.pop("init", False) else None
+    fn = diffusion.ddim_sample_loop if ddim else diffusion.p_sample_loop
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    got = fn(cfg, (B, 9, 3, 34), clip_denoised=kw.pop("clip_denoised", False), model_kwargs={"y": y},
+             init_image=init, progress=False, **kw)
+    assert diffusion.noise_source.pos == len(tape.record)            # same number of draws
+    _close(got, want)
+    _close(got, golden_ted["loop_" + tag])                           # and vs the reference itself
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_whole_loop_beat(impl, golden_beat):
+    dims, sd, cfg, diffusion = build("beat", "ddim100", impl=impl)
+    want, tape = run_oracle_loop("ddim100", golden_beat, dims, sd)
+    diffusion.noise_source = ls.ReplayNoise(tape.record)
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    got = diffusion.ddim_sample_loop(cfg, (2, 47, 6, 34), clip_denoised=False, model_kwargs={"y": y})
+    _close(got, golden_beat["loop_ddim100"])
+    _close(got, want)
+
+
+def test_same_seed_rng_order_and_layout_on_device():
+    """Draw order + memory layout parity: with the oracle's tape drawing from the CUDA
+    generator, the product's own torch draws under the same seed must be identical."""
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    tab, tmap = schedule_oracle.build("cosine", 1000, "ddim100")
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    shape = (3, 9, 3, 34)
+
+    class CudaTape(sampler_oracle.NoiseTape):
+        def __init__(self):
+            self.replay, self.record, self.gen, self.device = None, [], None, DEV
+
+        def draw(self, *s):
+            self.record.append(torch.randn(*s, device=DEV))
+            return self.record[-1]
+
+        def draw_like(self, x):
+            self.record.append(torch.randn_like(x))
+            return self.record[-1]
+
+    orig_pick = sampler_oracle._pick
+    sampler_oracle._pick = lambda table, i: orig_pick(table, i).to(DEV)
+    try:
+        torch.manual_seed(77)
+        tape = CudaTape()
+        with torch.no_grad():
+            want = sampler_oracle.sample_loop(sd_dev, tab, tmap, shape, synthetic.synth_cond(dims, 3, device=DEV),
+                                              tape, ddim=False, eta=0.0, skip_timesteps=94)
+    finally:
+        sampler_oracle._pick = orig_pick
+    torch.manual_seed(77)
+    got = diffusion.p_sample_loop(cfg, shape, clip_denoised=False,
+                                  model_kwargs={"y": synthetic.synth_cond(dims, 3, device=DEV)}, skip_timesteps=94)
+    _close(got, want)
+
+
+def test_progressive_generator_and_dump_steps():
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    torch.manual_seed(1)
+    outs = list(diffusion.p_sample_loop_progressive(cfg, (2, 9, 3, 34), clip_denoised=False,
+                                                    model_kwargs={"y": y}, skip_timesteps=95))
+    assert len(outs) == 5 and set(outs[0]) == {"sample", "pred_xstart"}
+    torch.manual_seed(1)
+    dump = diffusion.p_sample_loop(cfg, (2, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y},
+                                   skip_timesteps=95, dump_steps=[0, 4])
+    assert len(dump) == 2
+    assert torch.equal(dump[0], outs[0]["pred_xstart"]) and torch.equal(dump[1], outs[4]["pred_xstart"])
+    with pytest.raises(NotImplementedError):
+        diffusion.ddim_sample_loop(cfg, (2, 9, 3, 34), model_kwargs={"y": y}, dump_steps=[0])
+
+
+def test_generic_route_with_python_hooks_matches_fused():
+    """denoised_fn forces the generic route (model called like in the reference + torch
+    elementwise ops); with an identity hook it must reproduce the fused route."""
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    torch.manual_seed(5)
+    a = diffusion.ddim_sample_loop(cfg, (2, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y},
+                                   skip_timesteps=96, eta=0.5)
+    torch.manual_seed(5)
+    b = diffusion.ddim_sample_loop(cfg, (2, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y},
+                                   skip_timesteps=96, eta=0.5, denoised_fn=lambda v: v)
+    _close(a, b, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_full_size_properties_b512(impl):
+    """BASELINE config 2 shape (TED, B=512): size-independent properties.
+    (1) batch independence: clip b of the big batch == the same clip run in a batch of 4;
+    (2) guidance linearity: scale=0 -> uncond output, scale=1 -> cond output;
+    (3) determinism: two runs with the same inputs are bit-identical."""
+    dims, sd, cfg, diffusion = build("ted", "", impl=impl)
+    B = 512
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 9, 3, 34, generator=g).to(DEV)
+    e_c = torch.randn(B, 1, 512, generator=g).to(DEV)
+    e_u = torch.randn(B, 1, 512, generator=g).to(DEV)
+    nz = torch.randn(B, 9, 3, 34, generator=g).to(DEV)
+    eng = cfg.model.engine(B)
+    eng.set_cond(y, force=True)
+    p = diffusion.step_params(700, ddim=False, clip_denoised=False)
+    xp, x0 = torch.empty_like(x), torch.empty_like(x)
+    eng.step(p, x, e_c, e_u, nz, y["scale"], xp, x0)
+    xp2, x02 = torch.empty_like(x), torch.empty_like(x)
+    eng.step(p, x, e_c, e_u, nz, y["scale"], xp2, x02)
+    assert torch.equal(xp, xp2) and torch.equal(x0, x02)
+    assert torch.isfinite(xp).all()
+    # batch independence on 4 scattered clips
+    idx = torch.tensor([0, 129, 300, 511])
+    ys = {k: (v[idx.to(v.device)].clone() if torch.is_tensor(v) else v) for k, v in
+          synthetic.synth_cond(dims, B, device=DEV).items()}
+    eng.set_cond(ys, force=True)
+    xs, x0s = torch.empty(4, 9, 3, 34, device=DEV), torch.empty(4, 9, 3, 34, device=DEV)
+    di = idx.to(DEV)
+    eng.step(p, x[di].contiguous(), e_c[di].contiguous(), e_u[di].contiguous(), nz[di].contiguous(), ys["scale"],
+             xs, x0s)
+    _close(xs, xp[di], rtol=1e-5, atol=1e-5)
+    # oracle on those 4 clips
+    tab, tmap = schedule_oracle.build("cosine", 1000, "")
+    yc = {k: (v[idx].clone() if torch.is_tensor(v) else v) for k, v in synthetic.synth_cond(dims, B).items()}
+    tape = sampler_oracle.NoiseTape(replay=[e_c[di].cpu(), e_u[di].cpu(), nz[di].cpu()])
+    with torch.no_grad():
+        want, want0 = sampler_oracle.p_sample_step(sd, tab, tmap, x[di].cpu(), 700, yc, tape, 9, 3)
+    _close(xs, want)
+    _close(x0s, want0)
+    # guidance linearity
+    eng.set_cond(ys, force=True)
+    t4 = torch.full((4,), 700, device=DEV)
+    outs = {}
+    for s in (0.0, 1.0, 2.0):
+        outs[s] = eng.cfg_forward(x[di], t4, e_c[di], e_u[di], torch.full((4,), s, device=DEV))
+    oc, _, _ = eng.model_forward(x[di], t4, False, e_c[di])
+    ou, _, _ = eng.model_forward(x[di], t4, True, e_u[di])
+    _close(outs[0.0], ou, rtol=1e-5, atol=1e-5)
+    _close(outs[1.0], oc, rtol=1e-4, atol=1e-4)
+    _close(outs[2.0], ou + 2 * (oc - ou), rtol=1e-4, atol=1e-4)
+
+
+def test_error_paths():
+    from livelyspeaker_b200._cabi import LsError
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    eng = cfg.model.engine(2)
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    eng.set_cond(y)
+    x = torch.zeros(3, 9, 3, 34, device=DEV)
+    with pytest.raises(LsError):     # batch differs from the precomputed cond
+        eng.cfg_forward(x, torch.zeros(3, dtype=torch.long, device=DEV), torch.zeros(3, 1, 512, device=DEV),
+                        torch.zeros(3, 1, 512, device=DEV), torch.ones(3, device=DEV))
+    with pytest.raises(LsError):     # unknown key
+        eng.load_state_dict({"bogus.weight": torch.zeros(3)})
+    bad = dict(sd)
+    bad["input_mapping.bias"] = torch.zeros(7)
+    with pytest.raises(LsError):     # shape mismatch
+        eng.load_state_dict(bad)
+    p = diffusion.step_params(5, ddim=True)
+    p.t_model = 5000
+    xg = torch.zeros(2, 9, 3, 34, device=DEV)
+    with pytest.raises(LsError):     # timestep outside the embedding table
+        eng.load_state_dict(sd)
+        eng.set_cond(y, force=True)
+        eng.step(p, xg, torch.zeros(2, 1, 512, device=DEV), torch.zeros(2, 1, 512, device=DEV), xg, y["scale"],
+                 torch.empty_like(xg), None)

@@ -1,0 +1,139 @@
+"""The oracle against the fixtures the REFERENCE produced (tests/golden/make_golden.py).
+This is what licenses using oracle/ as the checker in the GPU parity tests."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import ATOL, RTOL
+from livelyspeaker_b200 import synthetic
+from oracle import rag_oracle, sampler_oracle, schedule_oracle
+
+TIGHT = dict(rtol=1e-5, atol=2e-5)     # oracle vs reference: same fp32 ops, same order
+
+
+def _close(a, b, **kw):
+    np.testing.assert_allclose(np.asarray(a), np.asarray(b), **(kw or TIGHT))
+
+
+@pytest.fixture(scope="module")
+def ted():
+    dims = synthetic.TED
+    return dims, synthetic.synth_state_dict(dims, seed=1)
+
+
+def test_synthetic_weights_are_the_ones_the_fixtures_used(golden_ted, golden_beat, ted):
+    for dims, g in ((synthetic.TED, golden_ted), (synthetic.BEAT, golden_beat)):
+        sd = synthetic.synth_state_dict(dims, seed=1)
+        s = sum(float(v.double().abs().sum()) for v in sd.values())
+        assert abs(s - float(g["weights_abs_sum"])) < 1e-6 * s
+
+
+def test_ops(golden_ted, ted):
+    dims, sd = ted
+    y = synthetic.synth_cond(dims, 2)
+    with torch.no_grad():
+        _close(rag_oracle.wav_encoder(sd, y["audio_input"]), golden_ted["wavenc_out"])
+        hx = torch.from_numpy(golden_ted["block_in"])
+        _close(rag_oracle.ln_spatial(hx, sd["backbone.mlps.3.block1.0.alpha"], sd["backbone.mlps.3.block1.0.beta"]),
+               golden_ted["ln_out"])
+        tt = torch.from_numpy(golden_ted["temb_t"])
+        emb = rag_oracle.timestep_embed(sd, tt)
+        _close(emb, golden_ted["temb_out"])
+        _close(rag_oracle.mlp_block(sd, 3, hx, emb), golden_ted["block_out"])
+        _close(rag_oracle.trans_mlp(sd, hx, tt), golden_ted["backbone_out"])
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_forward_and_cfg(name, golden_ted, golden_beat):
+    g = golden_ted if name == "ted" else golden_beat
+    dims = synthetic.dims_for(name)
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    x, t = torch.from_numpy(g["fwd_x"]), torch.from_numpy(g["fwd_t"])
+    with torch.no_grad():
+        for tag, unc in (("cond", False), ("uncond", True)):
+            y = synthetic.synth_cond(dims, 2)
+            if unc:
+                y["uncond"] = True
+            eps = torch.randn(2, 1, 512, generator=torch.Generator().manual_seed(11))
+            o = rag_oracle.rag_forward(sd, x, t, y, eps, dims.njoints, dims.nfeats)
+            for key in ("output", "z_mu", "z_logvar"):
+                _close(o[key], g["fwd_%s_%s" % (tag, key)])
+            assert float(y["origin_x"][..., 4:].abs().max()) == 0.0
+        tape = sampler_oracle.NoiseTape(seed=12)
+        o = rag_oracle.cfg_forward(sd, x, t, synthetic.synth_cond(dims, 2), tape.draw(2, 1, 512),
+                                   tape.draw(2, 1, 512), dims.njoints, dims.nfeats)
+        _close(o, g["cfg_out"])
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_single_steps(name, golden_ted, golden_beat):
+    g = golden_ted if name == "ted" else golden_beat
+    dims = synthetic.dims_for(name)
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    xs = torch.from_numpy(g["step_x"])
+    tab_full, map_full = schedule_oracle.build("cosine", 1000, "")
+    tab_ddim, map_ddim = schedule_oracle.build("cosine", 1000, "ddim100")
+    with torch.no_grad():
+        for i in (999, 0):
+            tape = sampler_oracle.NoiseTape(seed=100 + i)
+            s, p0 = sampler_oracle.p_sample_step(sd, tab_full, map_full, xs, i, synthetic.synth_cond(dims, 2), tape,
+                                                 dims.njoints, dims.nfeats)
+            _close(s, g["pstep%d_sample" % i])
+            _close(p0, g["pstep%d_x0" % i])
+        for i, eta in ((57, 0.5), (0, 0.0)):
+            tape = sampler_oracle.NoiseTape(seed=200 + i)
+            s, p0 = sampler_oracle.ddim_step(sd, tab_ddim, map_ddim, xs, i, synthetic.synth_cond(dims, 2), tape,
+                                             dims.njoints, dims.nfeats, eta=eta)
+            tag = "dstep%d_eta%d" % (i, int(eta * 10))
+            _close(s, g[tag + "_sample"])
+            _close(p0, g[tag + "_x0"])
+
+
+LOOPS = {   # tag: (respacing, steps, ddim, seed, batch, kwargs)
+    "ddim100": ("ddim100", 1000, True, 233, 2, {}),
+    "anc100": ("100", 1000, False, 234, 2, {}),
+    "ddim100_sdedit": ("ddim100", 1000, True, 235, 2, {"skip_timesteps": 80, "init": True}),
+    "ddim100_eta05_clip": ("ddim100", 1000, True, 236, 2, {"eta": 0.5, "clip_denoised": True}),
+    "anc100_constnoise": ("100", 1000, False, 237, 2, {"const_noise": True}),
+    "anc100_skip60": ("100", 1000, False, 238, 2, {"skip_timesteps": 60}),
+    "t100_b1": ("", 100, False, 239, 1, {}),
+}
+
+
+def run_oracle_loop(tag, g, dims, sd):
+    spec, steps, ddim, seed, B, kw = LOOPS[tag]
+    kw = dict(kw)
+    tab, tmap = schedule_oracle.build("cosine", steps, spec)
+    init = torch.from_numpy(g["init_image"]) if kw.pop("init", False) else None
+    tape = sampler_oracle.NoiseTape(seed=seed)
+    with torch.no_grad():
+        out = sampler_oracle.sample_loop(sd, tab, tmap, (B, dims.njoints, dims.nfeats, 34),
+                                         synthetic.synth_cond(dims, B), tape, ddim=ddim, init_image=init, **kw)
+    return out, tape
+
+
+@pytest.mark.parametrize("tag", ["ddim100", "anc100", "ddim100_sdedit", "ddim100_eta05_clip", "anc100_constnoise",
+                                 "anc100_skip60", "t100_b1"])
+def test_whole_loops_ted(tag, golden_ted, ted):
+    dims, sd = ted
+    out, tape = run_oracle_loop(tag, golden_ted, dims, sd)
+    _close(out, golden_ted["loop_" + tag])
+    # and within the product tolerance by a wide margin
+    np.testing.assert_allclose(out.numpy(), golden_ted["loop_" + tag], rtol=RTOL, atol=ATOL)
+
+
+def test_whole_loop_beat(golden_beat):
+    dims = synthetic.BEAT
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    out, _ = run_oracle_loop("ddim100", golden_beat, dims, sd)
+    _close(out, golden_beat["loop_ddim100"])
+
+
+def test_noise_tape_layout_rule():
+    """From the 2nd step on the step noise is drawn in [F,B,J,D] memory order (the layout
+    OutputProcess' permute gives x_t); the tape must reproduce torch's behaviour."""
+    x = torch.empty(34, 2, 9, 3).permute(1, 2, 3, 0)
+    a = sampler_oracle.NoiseTape(seed=3).draw_like(x)
+    torch.manual_seed(3)
+    b = torch.randn_like(x)
+    assert torch.equal(a, b) and a.stride() == x.stride()
