@@ -90,7 +90,7 @@ def test_precompute_buffers_and_origin_side_effect():
     tt = torch.tensor([0, 17, 990, 999])
     with torch.no_grad():
         want = rag_oracle.timestep_embed(sd, tt)
-    _close(eng.debug_buffer(4).view(1000, 512)[tt.to(DEV)], want)
+    _close(eng.debug_buffer(4).view(1000, 512)[tt.to(DEV)], want.squeeze(1))
 
 
 @pytest.mark.parametrize("name", ["ted", "beat"])
@@ -199,6 +199,9 @@ def test_same_seed_rng_order_and_layout_on_device():
 
     orig_pick = sampler_oracle._pick
     sampler_oracle._pick = lambda table, i: orig_pick(table, i).to(DEV)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False        # the oracle's conv1d must stay fp32 on the GPU
+    torch.backends.cuda.matmul.allow_tf32 = False
     try:
         torch.manual_seed(77)
         tape = CudaTape()
@@ -207,6 +210,7 @@ def test_same_seed_rng_order_and_layout_on_device():
                                               tape, ddim=False, eta=0.0, skip_timesteps=94)
     finally:
         sampler_oracle._pick = orig_pick
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     torch.manual_seed(77)
     got = diffusion.p_sample_loop(cfg, shape, clip_denoised=False,
                                   model_kwargs={"y": synthetic.synth_cond(dims, 3, device=DEV)}, skip_timesteps=94)
