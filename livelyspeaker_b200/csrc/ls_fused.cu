@@ -1,9 +1,595 @@
-// placeholder: tcgen05 path not built yet
+// The fused denoising step: ONE persistent sm_100a kernel per step.
+//
+//   _WrappedModel + ClassifierFreeSampleModel + RAG.forward (minus the hoisted terms) +
+//   p_mean_variance + p_sample / ddim_sample of the reference
+//   (respace.py:118-130, cfg_sampler.py:24-31, RAG.py:98-133, mlp_module.py:37-91,
+//    gaussian_diffusion.py:284-399, 507-558, 745-798) - see DESIGN.md "fused step kernel".
+//
+// Work unit (tile) = one clip, both guidance passes: 2*S token rows (S = 35 TED / 36 BEAT).
+// All GEMMs run TRANSPOSED on the tensor cores, D^T[channel, row] = W[channel, k] * U^T[k, row]:
+//   M = 128 output channels (4 M-tiles for d = 512), N = 80 rows (2*S padded), K = channels.
+// so the TMEM lane of an accumulator element is its CHANNEL and the column is its ROW:
+//   * each of the 512 epilogue threads owns one channel and keeps the fp32 residual stream
+//     h[row] of that channel in REGISTERS for the whole 8-layer stack;
+//   * TMEM holds only accumulators (4 M-tiles x 80 columns);
+//   * shared memory holds the bf16 hi/lo operand tile U (LayerNorm output) - the very same
+//     bytes serve as the K-major B operand of the channel-mix GEMM and as the MN-major A
+//     operand of the token-mix GEMM (ls_tc.cuh, validated by umma_probe.cu) - plus a
+//     2-slot ring of weight stages streamed from L2 by 1-D bulk async copies.
+// Precision: PRECISE = bf16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate) meets the
+// rtol 1e-3 / atol 1e-4 parity bar; !PRECISE = plain bf16 operands (fast mode).
+//
+// Warp roles (18 warps): 0-15 epilogue (thread id == channel), 16 weight producer,
+// 17 MMA issuer + TMEM owner.
+#include <cuda_bf16.h>
+#include <cstdlib>
+
 #include "ls_internal.cuh"
-int lsf_init(ls_handle*, cudaStream_t) { return 1; }
-void lsf_destroy(ls_handle*) {}
-int lsf_available(const ls_handle*) { return 0; }
-int lsf_step(ls_handle* h, int, const ls_step_params*, int, const float*, const float*, const float*, const float*,
-             int64_t, int64_t, int64_t, const float*, float*, float*, cudaStream_t) {
-  return ls_fail(h, LS_EUNSUPPORTED, "tcgen05 path not built");
+#include "ls_tc.cuh"
+#include "ls_update.cuh"
+
+using namespace lstc;
+
+namespace {
+
+constexpr int NT_EPI = 512;
+constexpr int NT_ALL = 576;
+constexpr int NROW = 80;                       // MMA N (rows of a tile, padded)
+constexpr int RGS = 9;                         // 8-row groups stored per 64-channel block (72 rows)
+constexpr uint32_t CBS = RGS * 1024;           // bytes between 64-channel blocks of U
+constexpr uint32_t U_BYTES = 8 * CBS;          // one of U_hi / U_lo
+constexpr uint32_t SLOT = 32768;               // ring slot = tape stage pitch
+constexpr int NSLOT = 2;
+constexpr uint32_t W_HALF = 16384;             // 128 x 64 bf16 weight block (hi or lo)
+constexpr uint32_t WBLK_BLK = 10 * 1024;       // token-mix weights: 80 rows x 64 k
+constexpr uint32_t WBLK_BYTES = 2 * WBLK_BLK;  // k padded to 128
+
+// shared memory map (offsets from a 1024-aligned base)
+constexpr uint32_t OFF_UHI = 0;
+constexpr uint32_t OFF_ULO = U_BYTES;
+constexpr uint32_t OFF_PAD = 2 * U_BYTES;               // 1024 zero bytes: row group 9 of the last block
+constexpr uint32_t OFF_RING = OFF_PAD + 1024;
+constexpr uint32_t OFF_PART = OFF_RING + NSLOT * SLOT;  // [16 warps][72 rows] float2 LN partial sums
+constexpr uint32_t OFF_STATS = OFF_PART + 16 * 72 * 8;  // [72] float2 (mean, rstd)
+constexpr uint32_t OFF_BTOK = OFF_STATS + 72 * 8;       // [72] float token-mix bias
+constexpr uint32_t OFF_BARS = OFF_BTOK + 72 * 4;        // mbarriers
+constexpr uint32_t OFF_TMEM = OFF_BARS + 16 * 8;
+constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
+constexpr uint32_t SMEM_DYN = SMEM_USED + 1024;         // + alignment slack
+
+enum { BAR_FULL0 = 0, BAR_EMPTY0 = 2, BAR_UREADY = 4, BAR_ACC0 = 5 };   // indices into the mbarrier array
+
+struct FusedParams {
+  const uint8_t* tape;     // weight stages, SLOT bytes apart
+  int n_layers, JD, KIN, MH, B;
+  int dbg;                 // debug: bit0 ch w_lo*u_hi, bit1 ch w_hi*u_lo, bit2 tok u_lo*w_hi, bit3 tok u_hi*w_lo
+  LsWeights w;
+  const float* A; const float* P; const float* z_mu; const float* z_lv; const float* emo_tok;
+  const float* x_t; const float* eps_c; const float* eps_u; const float* noise; const float* scale;
+  long long nsb, nsj, nsf;
+  float* x_prev; float* pred_x0;
+  ls_step_params sp;
+};
+
+__device__ __forceinline__ float silu_fast(float z) { return z * __frcp_rn(1.f + __expf(-z)); }
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// hi/lo bf16 split of v, stored at byte offset `off` of U_hi (and U_lo)
+__device__ int g_dbg_lo = 1;
+template <bool PRECISE>
+__device__ __forceinline__ void store_split(uint8_t* ubase, uint32_t off, float v) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  *reinterpret_cast<__nv_bfloat16*>(ubase + off) = hi;
+  if (PRECISE && g_dbg_lo) {
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    *reinterpret_cast<__nv_bfloat16*>(ubase + OFF_ULO + off) = lo;
+  }
+}
+
+// Per-row (sum, sum of squares) over the 512 channels -> stats[row] = (mean, 1/std).
+// h[] holds this thread's channel; `shift` rows come from the previous stats (robust
+// single-pass variance), or 0 when use_shift is false.
+template <int R>
+__device__ __forceinline__ void ln_stats(const float (&h)[72], uint8_t* sm, bool use_shift) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float2* part = reinterpret_cast<float2*>(sm + OFF_PART);
+  float2* stats = reinterpret_cast<float2*>(sm + OFF_STATS);
+#pragma unroll
+  for (int g = 0; g < 9; ++g) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = 8 * g + j;
+      float d = 0.f;
+      if (n < R) d = h[n] - (use_shift ? stats[n].x : 0.f);
+      s[j] = d;
+      q[j] = d * d;
+    }
+    // halving butterfly: after the three steps lane bits (4,3,2) select the row
+#pragma unroll
+    for (int step = 0; step < 3; ++step) {
+      const int half = 4 >> step;            // 4, 2, 1 values kept
+      const int xm = 16 >> step;             // xor 16, 8, 4
+      const bool up = (lane & xm) != 0;
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const float send_s = up ? s[j] : s[j + half];
+        const float send_q = up ? q[j] : q[j + half];
+        const float keep_s = up ? s[j + half] : s[j];
+        const float keep_q = up ? q[j + half] : q[j];
+        s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, xm);
+        q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, xm);
+      }
+    }
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], 2);
+    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+    q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+    if ((lane & 3) == 0) {
+      const int row = 8 * g + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      part[warp * 72 + row] = make_float2(s[0], q[0]);
+    }
+  }
+  epi_bar();
+  if (tid < R) {
+    float ss = 0.f, qq = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+      const float2 p = part[w * 72 + tid];
+      ss += p.x;
+      qq += p.y;
+    }
+    const float sh = use_shift ? stats[tid].x : 0.f;
+    const float md = ss * (1.f / 512.f);
+    const float var = fmaxf(qq * (1.f / 512.f) - md * md, 0.f);
+    stats[tid] = make_float2(sh + md, rsqrtf(var + 1e-5f));
+  }
+  epi_bar();
+}
+
+// LayerNorm of h -> bf16 (hi, lo) operand tile.  pre = smem address of (row 0, channel c)
+// with the chunk bits at [4,7): row n lives at (pre ^ ((n&7)<<4)) + (n&7)*128 + (n>>3)*1024.
+template <int R, bool PRECISE>
+__device__ __forceinline__ void ln_store(const float (&h)[72], uint8_t* sm, uint32_t pre_off, float alpha, float beta) {
+  const float2* stats = reinterpret_cast<const float2*>(sm + OFF_STATS);
+#pragma unroll
+  for (int n = 0; n < R; ++n) {
+    const float2 st = stats[n];
+    const float u = fmaf((h[n] - st.x) * st.y, alpha, beta);
+    const uint32_t off = (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
+    store_split<PRECISE>(sm, off, u);
+  }
+}
+
+// Walk the accumulator columns [0, R) of this thread's TMEM lane in chunks of 16 (+8) and hand
+// (row, value) to f with compile-time row indices.  Must be executed by whole warps.
+template <int R, class F>
+__device__ __forceinline__ void for_acc(uint32_t taddr, F&& f) {
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    float v[16];
+    tmem_ld16(taddr + c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c0 + j < R) f(c0 + j, v[j]);
+  }
+  {
+    float v[8];
+    tmem_ld8(taddr + 64, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (64 + j < R) f(64 + j, v[j]);
+  }
+}
+
+template <int S, bool PRECISE>
+__global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams p) {
+  constexpr int R = 2 * S;            // real rows of a tile
+  constexpr int NPRE = S - LS_F;      // prefix tokens per pass
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BARS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup ----------------------------------------------------------------
+  for (uint32_t i = tid * 16; i < OFF_RING; i += NT_ALL * 16) *reinterpret_cast<uint4*>(sm + i) = make_uint4(0, 0, 0, 0);
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&bars[BAR_FULL0 + s], 1);
+      mbar_init(&bars[BAR_EMPTY0 + s], 1);
+    }
+    mbar_init(&bars[BAR_UREADY], NT_EPI);
+    for (int m = 0; m < 4; ++m) mbar_init(&bars[BAR_ACC0 + m], 1);
+    mbar_fence_init();
+  }
+  if (warp == 17) tmem_alloc<512>(tmem_slot);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const int n_tiles = p.B;
+
+  if (warp == 16) {
+    // ================= weight producer: walks the tape once per tile =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t wbytes = (PRECISE && (p.dbg & 16)) ? 2 * W_HALF : W_HALF;
+      auto push = [&](uint32_t stage, uint32_t bytes) {
+        const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
+        mbar_wait(&bars[BAR_EMPTY0 + slot], ph ^ 1);
+        mbar_arrive_expect_tx(&bars[BAR_FULL0 + slot], bytes);
+        bulk_g2s(sm + OFF_RING + slot * SLOT, p.tape + (size_t)stage * SLOT, bytes, &bars[BAR_FULL0 + slot]);
+        ++it;
+      };
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t st = 0;
+        for (int i = 0; i < 4 * p.KIN; ++i) push(st++, wbytes);
+        for (int l = 0; l < p.n_layers; ++l) {
+          push(st++, WBLK_BYTES);
+          if (PRECISE && !(p.dbg & 64)) push(st, WBLK_BYTES);
+          ++st;
+          for (int i = 0; i < 32; ++i) push(st++, wbytes);
+        }
+        for (int i = 0; i < 8 * p.MH; ++i) push(st++, wbytes);
+      }
+    }
+  } else if (warp == 17) {
+    // ================= MMA issuer ==========================================================
+    if (lane == 0) {
+      uint32_t it = 0, uphase = 0;
+      const uint32_t id_kk = idesc_bf16(128, NROW, 0, 0), id_mk = idesc_bf16(128, NROW, 1, 0);
+      const uint32_t u_hi = smem_u32(sm + OFF_UHI), u_lo = smem_u32(sm + OFF_ULO), ring = smem_u32(sm + OFF_RING);
+      auto wait_u = [&]() {
+        mbar_wait(&bars[BAR_UREADY], uphase & 1);
+        ++uphase;
+        if (p.dbg & 128) __nanosleep(3000);
+        tc_fence_after_sync();
+      };
+      // D[mt] (+)= W-stage[128 x 64] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
+      auto gemm_stage = [&](int mt, int kc, bool first) {
+        const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
+        mbar_wait(&bars[BAR_FULL0 + slot], ph);
+        tc_fence_after_sync();
+        const uint32_t wb = ring + slot * SLOT, d = tmem + (uint32_t)mt * NROW;
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) {
+          const uint64_t a_hi = smem_desc(wb + ks * 32, 16, 1024, SWZ_128B);
+          const uint64_t b_hi = smem_desc(u_hi + kc * CBS + ks * 32, 16, 1024, SWZ_128B);
+          umma_bf16(d, a_hi, b_hi, id_kk, (first && ks == 0) ? 0u : 1u);
+          if (PRECISE) {
+            const uint64_t a_lo = smem_desc(wb + W_HALF + ks * 32, 16, 1024, SWZ_128B);
+            const uint64_t b_lo = smem_desc(u_lo + kc * CBS + ks * 32, 16, 1024, SWZ_128B);
+            if (p.dbg & 1) umma_bf16(d, a_lo, b_hi, id_kk, 1u);
+            if (p.dbg & 2) umma_bf16(d, a_hi, b_lo, id_kk, 1u);
+          }
+        }
+        umma_commit(&bars[BAR_EMPTY0 + slot]);
+        ++it;
+      };
+      auto signal_acc = [&]() {
+        for (int m = 0; m < 4; ++m) umma_commit(&bars[BAR_ACC0 + m]);
+      };
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // input projection
+        wait_u();
+        for (int mt = 0; mt < 4; ++mt) {
+          for (int kc = 0; kc < p.KIN; ++kc) gemm_stage(mt, kc, kc == 0);
+          umma_commit(&bars[BAR_ACC0 + mt]);
+        }
+        for (int l = 0; l < p.n_layers; ++l) {
+          // token mix: D[mt][ch, row_out] = sum_row_in U^T[ch, row_in] * Wblk[row_out, row_in]
+          wait_u();
+          for (int half = 0; half < ((PRECISE && !(p.dbg & 64)) ? 2 : 1); ++half) {
+            const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
+            mbar_wait(&bars[BAR_FULL0 + slot], ph);
+            tc_fence_after_sync();
+            const uint32_t wb = ring + slot * SLOT;
+            for (uint32_t mt = 0; mt < 4; ++mt) {
+              const uint32_t d = tmem + mt * NROW;
+#pragma unroll
+              for (uint32_t ks = 0; ks < 5; ++ks) {
+                const uint64_t bd = smem_desc(wb + (ks >> 2) * WBLK_BLK + (ks & 3) * 32, 16, 1024, SWZ_128B);
+                const uint64_t a_hi = smem_desc(u_hi + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B);
+                if (half == 0) {
+                  umma_bf16(d, a_hi, bd, id_mk, ks == 0 ? 0u : 1u);
+                  if (PRECISE) {
+                    const uint64_t a_lo = smem_desc(u_lo + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B);
+                    if (p.dbg & 4) umma_bf16(d, a_lo, bd, id_mk, 1u);
+                  }
+                } else {
+                  if (p.dbg & 8) umma_bf16(d, a_hi, bd, id_mk, 1u);   // U_hi * Wblk_lo
+                }
+              }
+            }
+            umma_commit(&bars[BAR_EMPTY0 + slot]);
+            ++it;
+          }
+          signal_acc();
+          // channel mix
+          wait_u();
+          for (int mt = 0; mt < 4; ++mt) {
+            for (int kc = 0; kc < 8; ++kc) gemm_stage(mt, kc, kc == 0);
+            umma_commit(&bars[BAR_ACC0 + mt]);
+          }
+        }
+        // output head (M-tiles beyond MH carry no work but still flip their barrier)
+        wait_u();
+        for (int mt = 0; mt < 4; ++mt) {
+          if (mt < p.MH)
+            for (int kc = 0; kc < 8; ++kc) gemm_stage(mt, kc, kc == 0);
+          umma_commit(&bars[BAR_ACC0 + mt]);
+        }
+      }
+    }
+  } else {
+    // ================= epilogue: thread == channel ==========================================
+    const int c = tid;
+    const int mt = warp >> 2;
+    const uint32_t lane_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * NROW;
+    const uint32_t pre_off = (uint32_t)(c >> 6) * CBS + (uint32_t)(((c & 63) >> 3) << 4) + (uint32_t)(c & 7) * 2u;
+    float* btok_s = reinterpret_cast<float*>(sm + OFF_BTOK);
+    const float emb = p.w.emb_table[(size_t)p.sp.t_model * LS_D + c];
+    uint32_t aphase = 0;
+    auto wait_acc = [&]() {
+      mbar_wait(&bars[BAR_ACC0 + mt], aphase & 1);
+      ++aphase;
+      __syncwarp();                 // the spin loop may leave the warp diverged; tcgen05.ld is .aligned
+      tc_fence_after_sync();
+    };
+    auto publish_u = [&]() {        // operand tile written (and accumulators consumed)
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&bars[BAR_UREADY]);
+    };
+    float h[72];
+
+    for (int b = blockIdx.x; b < n_tiles; b += gridDim.x) {
+      // ---- X operand: x_t[b] (hi, lo) into rows p*S + NPRE + f, k = j ----------------------
+      const float* xb = p.x_t + (size_t)b * p.JD * LS_F;
+      for (int i = tid; i < p.JD * LS_F; i += NT_EPI) {
+        const int j = i / LS_F, f = i - j * LS_F;
+        const float v = xb[i];
+        store_split<PRECISE>(sm, tile_off(NPRE + f, j, CBS), v);
+        store_split<PRECISE>(sm, tile_off(S + NPRE + f, j, CBS), v);
+      }
+      publish_u();
+      // ---- residual stream init: hoisted terms now, projection result when it lands --------
+      {
+        const float mu = p.z_mu[(size_t)b * LS_D + c], sd = __expf(0.5f * p.z_lv[(size_t)b * LS_D + c]);
+        h[0] = fmaf(p.eps_c[(size_t)b * LS_D + c], sd, mu);
+        h[S] = fmaf(p.eps_u[(size_t)b * LS_D + c], sd, mu);
+        if (NPRE == 2) h[1] = h[S + 1] = p.emo_tok[(size_t)b * LS_D + c];
+        const float* Pb = p.P + (size_t)b * LS_F * LS_D + c;
+        const float* Ab = p.A + (size_t)b * LS_F * LS_D + c;
+#pragma unroll
+        for (int f = 0; f < LS_F; ++f) {
+          const float pv = Pb[f * LS_D];
+          h[S + NPRE + f] = pv;
+          h[NPRE + f] = pv + Ab[f * LS_D];
+        }
+      }
+      wait_acc();
+      for_acc<R>(lane_taddr, [&](int n, float v) {
+        if ((n % S) >= NPRE) h[n] += v;          // prefix-token rows keep their direct values
+      });
+
+      for (int l = 0; l < p.n_layers; ++l) {
+        const LsLayerW L = p.w.layer[l];
+        const float a1 = L.ln1_a[c], b1 = L.ln1_b[c], a2 = L.ln2_a[c], b2 = L.ln2_b[c], bch = L.b_ch[c];
+        if (tid < S) btok_s[tid] = btok_s[S + tid] = L.b_tok[tid];
+        // x = x + emb ; LN1 ; -> operand tile
+#pragma unroll
+        for (int n = 0; n < R; ++n) h[n] += emb;
+        if (l == 0) ln_stats<R>(h, sm, false);     // provisional means for the shift
+        ln_stats<R>(h, sm, true);
+        ln_store<R, PRECISE>(h, sm, pre_off, a1, b1);
+        publish_u();
+        // token mix epilogue: x = x + silu(conv + bias)
+        wait_acc();
+        for_acc<R>(lane_taddr, [&](int n, float v) { if (!(p.dbg & 256)) h[n] += silu_fast(v + btok_s[n]); });
+        ln_stats<R>(h, sm, true);
+        ln_store<R, PRECISE>(h, sm, pre_off, a2, b2);
+        publish_u();
+        // channel mix epilogue: x = x + silu(linear + bias)
+        wait_acc();
+        for_acc<R>(lane_taddr, [&](int n, float v) { if (!(p.dbg & 512)) h[n] += silu_fast(v + bch); });
+      }
+
+      // ---- output head operand: plain hi/lo split of h -------------------------------------
+      // Every thread must be past its last wait_acc before U is overwritten: the channel-mix
+      // MMAs of the other M-tiles still read U until their own accumulator barrier fires.
+      epi_bar();
+#pragma unroll
+      for (int n = 0; n < R; ++n) {
+        const uint32_t off = (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
+        store_split<PRECISE>(sm, off, h[n]);
+      }
+      publish_u();
+      wait_acc();
+      if (warp * 32 < p.JD) {                    // warp-uniform: tcgen05.ld is .aligned
+        // h is dead: reuse it for the head outputs (lane = output feature j, column = row)
+        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] = v; });
+        if (c < p.JD) {
+          const float bo = p.w.b_out[c], sc = p.scale[b];
+          const size_t base = ((size_t)b * p.JD + c) * LS_F;
+          const float* nzp = p.noise ? p.noise + (size_t)b * p.nsb + (size_t)c * p.nsj : nullptr;
+          const bool use_noise = (p.sp.mode != 2) && p.sp.add_noise && nzp != nullptr;
+#pragma unroll
+          for (int f = 0; f < LS_F; ++f) {
+            const float oc = h[NPRE + f] + bo, ou = h[S + NPRE + f] + bo;
+            float x0 = ou + sc * (oc - ou);                       // cfg_sampler.py:31
+            const float nz = use_noise ? nzp[(size_t)f * p.nsf] : 0.f;
+            float xp = 0.f;
+            x0 = ls_sampler_update(p.sp, x0, p.x_t[base + f], nz, &xp);
+            if (p.pred_x0) p.pred_x0[base + f] = x0;
+            if (p.sp.mode != 2) p.x_prev[base + f] = xp;
+          }
+        }
+      }
+      // the next tile's X operand overwrites U: every head MMA has completed (wait_acc above)
+      tc_fence_before_sync();
+      epi_bar();
+    }
+  }
+  // ---- teardown ---------------------------------------------------------------------------
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 17) tmem_dealloc<512>(tmem);
+}
+
+// ---- weight tape ------------------------------------------------------------------------------
+// stage = [128 x 64] block of W (rows m0.., cols k0..) as K-major swizzle-128B images, hi then lo.
+__global__ void build_w_stage_kernel(const float* __restrict__ src, int rows, int cols, int ld, int m0, int k0,
+                                     uint8_t* __restrict__ dst) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 64; i += gridDim.x * blockDim.x) {
+    const int m = i >> 6, k = i & 63;
+    const float v = (m0 + m < rows && k0 + k < cols) ? src[(size_t)(m0 + m) * ld + k0 + k] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const uint32_t off = tile_off(m, k, 0);
+    *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(dst + W_HALF + off) = lo;
+  }
+}
+
+// token-mix stage pair: block-diagonal [80 x 128] (two passes share W_tok), K-major, hi stage then lo stage
+__global__ void build_wblk_kernel(const float* __restrict__ w_tok, int S, uint8_t* __restrict__ dst_hi,
+                                  uint8_t* __restrict__ dst_lo) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NROW * 128; i += gridDim.x * blockDim.x) {
+    const int n = i >> 7, k = i & 127;
+    float v = 0.f;
+    if (n < 2 * S && k < 2 * S && (n / S) == (k / S)) v = w_tok[(n % S) * S + (k % S)];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const uint32_t off = (uint32_t)(k >> 6) * WBLK_BLK + tile_off(n, k & 63, 0);
+    *reinterpret_cast<__nv_bfloat16*>(dst_hi + off) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(dst_lo + off) = lo;
+  }
+}
+
+struct FusedState {
+  uint8_t* tape = nullptr;
+  size_t tape_bytes = 0;
+  int KIN = 0, MH = 0, n_stages = 0;
+  int sm_count = 0;
+  bool attr_done[2][2] = {{false, false}, {false, false}};
+};
+
+template <int S, bool PRECISE>
+int launch_fused(ls_handle* h, FusedState* fs, const FusedParams& fp, cudaStream_t s) {
+  bool& done = fs->attr_done[S - 35][PRECISE ? 1 : 0];
+  if (!done) {
+    LS_CUDA(h, cudaFuncSetAttribute(fused_step_kernel<S, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN));
+    done = true;
+  }
+  const int grid = fp.B < fs->sm_count ? fp.B : fs->sm_count;
+  fused_step_kernel<S, PRECISE><<<grid, NT_ALL, SMEM_DYN, s>>>(fp);
+  LS_LAUNCH_CHECK(h);
+  return LS_OK;
+}
+
+}  // namespace
+
+int lsf_available(const ls_handle* h) { return h && h->fused != nullptr; }
+
+void lsf_destroy(ls_handle* h) {
+  if (h && h->fused) {
+    FusedState* fs = static_cast<FusedState*>(h->fused);
+    if (fs->tape) cudaFree(fs->tape);
+    delete fs;
+    h->fused = nullptr;
+  }
+}
+
+// Builds the weight tape.  Returns 0 when the fused path is usable, 1 when it is not built
+// for this geometry, < 0 on error.
+int lsf_init(ls_handle* h, cudaStream_t s) {
+  if (h->S != 35 && h->S != 36) return 1;
+  FusedState* fs = static_cast<FusedState*>(h->fused);
+  if (!fs) {
+    fs = new FusedState();
+    fs->KIN = (h->JD + 63) / 64;
+    fs->MH = (h->JD + 127) / 128;
+    if (fs->KIN > 8 || fs->MH > 4) {
+      delete fs;
+      return 1;
+    }
+    fs->n_stages = 4 * fs->KIN + h->cfg.n_layers * 34 + 8 * fs->MH;
+    fs->tape_bytes = (size_t)fs->n_stages * SLOT;
+    if (cudaMalloc(&fs->tape, fs->tape_bytes) != cudaSuccess) {
+      delete fs;
+      return ls_fail(h, LS_ENOMEM, "weight tape (%zu bytes)", (size_t)fs->n_stages * SLOT);
+    }
+    cudaDeviceGetAttribute(&fs->sm_count, cudaDevAttrMultiProcessorCount, h->cfg.device);
+    h->fused = fs;
+  }
+  LS_CUDA(h, cudaMemsetAsync(fs->tape, 0, fs->tape_bytes, s));
+  auto raw = [&](const std::string& k) -> const float* {
+    for (auto& r : h->raw)
+      if (r.key == k) return r.dev;
+    return nullptr;
+  };
+  const int IN = 2 * h->JD + 1 + LS_AF;
+  size_t st = 0;
+  const float* win = raw("input_mapping.weight");
+  for (int mt = 0; mt < 4; ++mt)
+    for (int kc = 0; kc < fs->KIN; ++kc) {
+      build_w_stage_kernel<<<16, 256, 0, s>>>(win, LS_D, h->JD, IN, mt * 128, kc * 64, fs->tape + st++ * SLOT);
+      LS_LAUNCH_CHECK(h);
+    }
+  for (int l = 0; l < h->cfg.n_layers; ++l) {
+    const std::string p = "backbone.mlps." + std::to_string(l) + ".";
+    build_wblk_kernel<<<16, 256, 0, s>>>(raw(p + "block1.1.weight"), h->S, fs->tape + st * SLOT, fs->tape + (st + 1) * SLOT);
+    LS_LAUNCH_CHECK(h);
+    st += 2;
+    const float* wch = raw(p + "block2.1.weight");
+    for (int mt = 0; mt < 4; ++mt)
+      for (int kc = 0; kc < 8; ++kc) {
+        build_w_stage_kernel<<<16, 256, 0, s>>>(wch, LS_D, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st++ * SLOT);
+        LS_LAUNCH_CHECK(h);
+      }
+  }
+  const float* wout = raw("output_process.poseFinal.weight");
+  for (int mt = 0; mt < fs->MH; ++mt)
+    for (int kc = 0; kc < 8; ++kc) {
+      build_w_stage_kernel<<<16, 256, 0, s>>>(wout, h->JD, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st++ * SLOT);
+      LS_LAUNCH_CHECK(h);
+    }
+  if ((int)st != fs->n_stages) return ls_fail(h, LS_EINVAL, "tape stage count mismatch");
+  return LS_OK;
+}
+
+int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const float* x_t, const float* eps_c,
+             const float* eps_u, const float* noise, int64_t sb, int64_t sj, int64_t sf, const float* scale,
+             float* x_prev, float* pred_x0, cudaStream_t s) {
+  FusedState* fs = static_cast<FusedState*>(h->fused);
+  if (!fs) return ls_fail(h, LS_EUNSUPPORTED, "tcgen05 path not available");
+  if (x_prev == x_t && p->mode != 2)
+    ;  // in-place update is fine: each element is read before it is written by the same thread
+  FusedParams fp{};
+  fp.tape = fs->tape;
+  fp.n_layers = h->cfg.n_layers;
+  fp.JD = h->JD;
+  fp.KIN = fs->KIN;
+  fp.MH = fs->MH;
+  fp.B = B;
+  {
+    const char* e = getenv("LS_DBG_MASK");
+    fp.dbg = e ? atoi(e) : 63;
+    int lo = (fp.dbg & 32) ? 1 : 0;
+    cudaMemcpyToSymbolAsync(g_dbg_lo, &lo, sizeof(int), 0, cudaMemcpyHostToDevice, s);
+  }
+  fp.w = h->w;
+  fp.A = h->A; fp.P = h->P; fp.z_mu = h->z_mu; fp.z_lv = h->z_lv; fp.emo_tok = h->emo_tok;
+  fp.x_t = x_t; fp.eps_c = eps_c; fp.eps_u = eps_u; fp.noise = noise; fp.scale = scale;
+  fp.nsb = sb; fp.nsj = sj; fp.nsf = sf;
+  fp.x_prev = x_prev; fp.pred_x0 = pred_x0;
+  fp.sp = *p;
+  if (h->S == 35) return precise ? launch_fused<35, true>(h, fs, fp, s) : launch_fused<35, false>(h, fs, fp, s);
+  return precise ? launch_fused<36, true>(h, fs, fp, s) : launch_fused<36, false>(h, fs, fp, s);
 }

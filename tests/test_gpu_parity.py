@@ -244,7 +244,7 @@ def test_generic_route_with_python_hooks_matches_fused():
     torch.manual_seed(5)
     b = diffusion.ddim_sample_loop(cfg, (2, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y},
                                    skip_timesteps=96, eta=0.5, denoised_fn=lambda v: v)
-    _close(a, b, rtol=1e-4, atol=1e-5)
+    _close(a, b)      # fused = tcgen05 bf16x3, generic = fp32 SIMT denoiser: same tolerance as vs the oracle
 
 
 @pytest.mark.parametrize("impl", IMPLS)
