@@ -87,6 +87,13 @@ def _f32(t, device):
     return t.contiguous()
 
 
+def _ref_layout(out):
+    """Give a dense [B,J,D,F] result the strides the reference's OutputProcess produces
+    (memory order [F,B,J,D], RAG.py:205-211): torch.randn_like on tensors derived from it
+    then draws in the same order as in the reference (DESIGN.md "RNG layout")."""
+    return out.permute(3, 0, 1, 2).contiguous().permute(1, 2, 3, 0)
+
+
 def _stream():
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -227,7 +234,7 @@ class Engine:
                                                   1 if uncond else 0, c_void_p(eps.data_ptr()),
                                                   c_void_p(out.data_ptr()), c_void_p(mu.data_ptr()),
                                                   c_void_p(lv.data_ptr()), _stream()))
-        return out, mu, lv
+        return _ref_layout(out), mu, lv
 
     def cfg_forward(self, x, t, eps_c, eps_u, scale):
         B = x.shape[0]
@@ -239,7 +246,7 @@ class Engine:
             self._check(self.lib.ls_cfg_forward(self.h, B, c_void_p(x.data_ptr()), c_void_p(t.data_ptr()),
                                                 c_void_p(eps_c.data_ptr()), c_void_p(eps_u.data_ptr()),
                                                 c_void_p(scale.data_ptr()), c_void_p(out.data_ptr()), _stream()))
-        return out
+        return _ref_layout(out)
 
     def step(self, params, x_t, eps_c, eps_u, noise, scale, x_prev, pred_x0):
         """One fused denoising step.  x_t / x_prev / pred_x0: dense fp32 [B,J,D,F] on the

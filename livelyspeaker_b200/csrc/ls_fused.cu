@@ -22,7 +22,6 @@
 // Warp roles (18 warps): 0-15 epilogue (thread id == channel), 16 weight producer,
 // 17 MMA issuer + TMEM owner.
 #include <cuda_bf16.h>
-#include <cstdlib>
 
 #include "ls_internal.cuh"
 #include "ls_tc.cuh"
@@ -62,7 +61,6 @@ enum { BAR_FULL0 = 0, BAR_EMPTY0 = 2, BAR_UREADY = 4, BAR_ACC0 = 5 };   // indic
 struct FusedParams {
   const uint8_t* tape;     // weight stages, SLOT bytes apart
   int n_layers, JD, KIN, MH, B;
-  int dbg;                 // debug: bit0 ch w_lo*u_hi, bit1 ch w_hi*u_lo, bit2 tok u_lo*w_hi, bit3 tok u_hi*w_lo
   LsWeights w;
   const float* A; const float* P; const float* z_mu; const float* z_lv; const float* emo_tok;
   const float* x_t; const float* eps_c; const float* eps_u; const float* noise; const float* scale;
@@ -76,14 +74,17 @@ __device__ __forceinline__ float silu_fast(float z) { return z * __frcp_rn(1.f +
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // hi/lo bf16 split of v, stored at byte offset `off` of U_hi (and U_lo)
-__device__ int g_dbg_lo = 1;
+__device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+}
+// u_s = shared-space address of U_hi
 template <bool PRECISE>
-__device__ __forceinline__ void store_split(uint8_t* ubase, uint32_t off, float v) {
+__device__ __forceinline__ void store_split(uint32_t u_s, uint32_t off, float v) {
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(ubase + off) = hi;
-  if (PRECISE && g_dbg_lo) {
+  sts_u16(u_s + off, __bfloat16_as_ushort(hi));
+  if (PRECISE) {
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    *reinterpret_cast<__nv_bfloat16*>(ubase + OFF_ULO + off) = lo;
+    sts_u16(u_s + OFF_ULO + off, __bfloat16_as_ushort(lo));
   }
 }
 
@@ -151,14 +152,15 @@ __device__ __forceinline__ void ln_stats(const float (&h)[72], uint8_t* sm, bool
 // LayerNorm of h -> bf16 (hi, lo) operand tile.  pre = smem address of (row 0, channel c)
 // with the chunk bits at [4,7): row n lives at (pre ^ ((n&7)<<4)) + (n&7)*128 + (n>>3)*1024.
 template <int R, bool PRECISE>
-__device__ __forceinline__ void ln_store(const float (&h)[72], uint8_t* sm, uint32_t pre_off, float alpha, float beta) {
+__device__ __forceinline__ void ln_store(const float (&h)[72], uint8_t* sm, uint32_t u_s, uint32_t pre_off, float alpha,
+                                         float beta) {
   const float2* stats = reinterpret_cast<const float2*>(sm + OFF_STATS);
 #pragma unroll
   for (int n = 0; n < R; ++n) {
     const float2 st = stats[n];
     const float u = fmaf((h[n] - st.x) * st.y, alpha, beta);
     const uint32_t off = (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
-    store_split<PRECISE>(sm, off, u);
+    store_split<PRECISE>(u_s, off, u);
   }
 }
 
@@ -218,7 +220,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
     // ================= weight producer: walks the tape once per tile =====================
     if (lane == 0) {
       uint32_t it = 0;
-      const uint32_t wbytes = (PRECISE && (p.dbg & 16)) ? 2 * W_HALF : W_HALF;
+      const uint32_t wbytes = PRECISE ? 2 * W_HALF : W_HALF;
       auto push = [&](uint32_t stage, uint32_t bytes) {
         const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
         mbar_wait(&bars[BAR_EMPTY0 + slot], ph ^ 1);
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
         for (int i = 0; i < 4 * p.KIN; ++i) push(st++, wbytes);
         for (int l = 0; l < p.n_layers; ++l) {
           push(st++, WBLK_BYTES);
-          if (PRECISE && !(p.dbg & 64)) push(st, WBLK_BYTES);
+          if (PRECISE) push(st, WBLK_BYTES);
           ++st;
           for (int i = 0; i < 32; ++i) push(st++, wbytes);
         }
@@ -247,7 +249,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
       auto wait_u = [&]() {
         mbar_wait(&bars[BAR_UREADY], uphase & 1);
         ++uphase;
-        if (p.dbg & 128) __nanosleep(3000);
         tc_fence_after_sync();
       };
       // D[mt] (+)= W-stage[128 x 64] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
@@ -264,8 +265,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
           if (PRECISE) {
             const uint64_t a_lo = smem_desc(wb + W_HALF + ks * 32, 16, 1024, SWZ_128B);
             const uint64_t b_lo = smem_desc(u_lo + kc * CBS + ks * 32, 16, 1024, SWZ_128B);
-            if (p.dbg & 1) umma_bf16(d, a_lo, b_hi, id_kk, 1u);
-            if (p.dbg & 2) umma_bf16(d, a_hi, b_lo, id_kk, 1u);
+            umma_bf16(d, a_lo, b_hi, id_kk, 1u);
+            umma_bf16(d, a_hi, b_lo, id_kk, 1u);
           }
         }
         umma_commit(&bars[BAR_EMPTY0 + slot]);
@@ -284,7 +285,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
         for (int l = 0; l < p.n_layers; ++l) {
           // token mix: D[mt][ch, row_out] = sum_row_in U^T[ch, row_in] * Wblk[row_out, row_in]
           wait_u();
-          for (int half = 0; half < ((PRECISE && !(p.dbg & 64)) ? 2 : 1); ++half) {
+          for (int half = 0; half < (PRECISE ? 2 : 1); ++half) {
             const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
             mbar_wait(&bars[BAR_FULL0 + slot], ph);
             tc_fence_after_sync();
@@ -299,10 +300,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
                   umma_bf16(d, a_hi, bd, id_mk, ks == 0 ? 0u : 1u);
                   if (PRECISE) {
                     const uint64_t a_lo = smem_desc(u_lo + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B);
-                    if (p.dbg & 4) umma_bf16(d, a_lo, bd, id_mk, 1u);
+                    umma_bf16(d, a_lo, bd, id_mk, 1u);
                   }
                 } else {
-                  if (p.dbg & 8) umma_bf16(d, a_hi, bd, id_mk, 1u);   // U_hi * Wblk_lo
+                  umma_bf16(d, a_hi, bd, id_mk, 1u);   // U_hi * Wblk_lo
                 }
               }
             }
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
     const uint32_t lane_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * NROW;
     const uint32_t pre_off = (uint32_t)(c >> 6) * CBS + (uint32_t)(((c & 63) >> 3) << 4) + (uint32_t)(c & 7) * 2u;
     float* btok_s = reinterpret_cast<float*>(sm + OFF_BTOK);
+    const uint32_t u_s = smem_u32(sm + OFF_UHI);
     const float emb = p.w.emb_table[(size_t)p.sp.t_model * LS_D + c];
     uint32_t aphase = 0;
     auto wait_acc = [&]() {
@@ -354,8 +356,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
       for (int i = tid; i < p.JD * LS_F; i += NT_EPI) {
         const int j = i / LS_F, f = i - j * LS_F;
         const float v = xb[i];
-        store_split<PRECISE>(sm, tile_off(NPRE + f, j, CBS), v);
-        store_split<PRECISE>(sm, tile_off(S + NPRE + f, j, CBS), v);
+        store_split<PRECISE>(u_s, tile_off(NPRE + f, j, CBS), v);
+        store_split<PRECISE>(u_s, tile_off(S + NPRE + f, j, CBS), v);
       }
       publish_u();
       // ---- residual stream init: hoisted terms now, projection result when it lands --------
@@ -387,17 +389,17 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
         for (int n = 0; n < R; ++n) h[n] += emb;
         if (l == 0) ln_stats<R>(h, sm, false);     // provisional means for the shift
         ln_stats<R>(h, sm, true);
-        ln_store<R, PRECISE>(h, sm, pre_off, a1, b1);
+        ln_store<R, PRECISE>(h, sm, u_s, pre_off, a1, b1);
         publish_u();
         // token mix epilogue: x = x + silu(conv + bias)
         wait_acc();
-        for_acc<R>(lane_taddr, [&](int n, float v) { if (!(p.dbg & 256)) h[n] += silu_fast(v + btok_s[n]); });
+        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(v + btok_s[n]); });
         ln_stats<R>(h, sm, true);
-        ln_store<R, PRECISE>(h, sm, pre_off, a2, b2);
+        ln_store<R, PRECISE>(h, sm, u_s, pre_off, a2, b2);
         publish_u();
         // channel mix epilogue: x = x + silu(linear + bias)
         wait_acc();
-        for_acc<R>(lane_taddr, [&](int n, float v) { if (!(p.dbg & 512)) h[n] += silu_fast(v + bch); });
+        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(v + bch); });
       }
 
       // ---- output head operand: plain hi/lo split of h -------------------------------------
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
 #pragma unroll
       for (int n = 0; n < R; ++n) {
         const uint32_t off = (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
-        store_split<PRECISE>(sm, off, h[n]);
+        store_split<PRECISE>(u_s, off, h[n]);
       }
       publish_u();
       wait_acc();
@@ -578,12 +580,6 @@ int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const fl
   fp.KIN = fs->KIN;
   fp.MH = fs->MH;
   fp.B = B;
-  {
-    const char* e = getenv("LS_DBG_MASK");
-    fp.dbg = e ? atoi(e) : 63;
-    int lo = (fp.dbg & 32) ? 1 : 0;
-    cudaMemcpyToSymbolAsync(g_dbg_lo, &lo, sizeof(int), 0, cudaMemcpyHostToDevice, s);
-  }
   fp.w = h->w;
   fp.A = h->A; fp.P = h->P; fp.z_mu = h->z_mu; fp.z_lv = h->z_lv; fp.emo_tok = h->emo_tok;
   fp.x_t = x_t; fp.eps_c = eps_c; fp.eps_u = eps_u; fp.noise = noise; fp.scale = scale;
