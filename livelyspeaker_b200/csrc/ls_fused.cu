@@ -19,8 +19,9 @@
 // Precision: PRECISE = bf16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate) meets the
 // rtol 1e-3 / atol 1e-4 parity bar; !PRECISE = plain bf16 operands (fast mode).
 //
-// Warp roles (18 warps): 0-15 epilogue (thread id == channel), 16 weight producer,
-// 17 MMA issuer + TMEM owner.
+// Warp roles (20 warps): 0-15 epilogue (thread id == channel), 16 weight producer,
+// 17 MMA issuer + TMEM owner, 18-19 idle; warps 16-19 give most of their registers to the
+// epilogue warps with setmaxnreg so the 70-row residual stream fits without spilling.
 #include <cuda_bf16.h>
 
 #include "ls_internal.cuh"
@@ -32,16 +33,17 @@ using namespace lstc;
 namespace {
 
 constexpr int NT_EPI = 512;
-constexpr int NT_ALL = 576;
+constexpr int NT_ALL = 640;                     // 16 epilogue warps + 1 producer + 1 MMA + 2 idle (register donors)
+constexpr int REGS_EPI = 112;                   // setmaxnreg budgets must conserve the launch allocation:
+constexpr int REGS_AUX = 32;                    // 512*112 + 128*32 == 640*96 (a larger total blocks forever in setmaxnreg.inc)
 constexpr int NROW = 80;                       // MMA N (rows of a tile, padded)
 constexpr int RGS = 9;                         // 8-row groups stored per 64-channel block (72 rows)
 constexpr uint32_t CBS = RGS * 1024;           // bytes between 64-channel blocks of U
 constexpr uint32_t U_BYTES = 8 * CBS;          // one of U_hi / U_lo
-constexpr uint32_t SLOT = 32768;               // ring slot = tape stage pitch
-constexpr int NSLOT = 2;
-constexpr uint32_t W_HALF = 16384;             // 128 x 64 bf16 weight block (hi or lo)
-constexpr uint32_t WBLK_BLK = 10 * 1024;       // token-mix weights: 80 rows x 64 k
-constexpr uint32_t WBLK_BYTES = 2 * WBLK_BLK;  // k padded to 128
+constexpr uint32_t SLOT = 16384;               // ring slot = tape stage pitch
+constexpr int NSLOT = 4;
+constexpr uint32_t W_HALF = 16384;             // 128 x 64 bf16 weight block (hi or lo) = one stage
+constexpr uint32_t WBLK_BLK = 10 * 1024;       // token-mix weights: 80 rows x 64 k = one stage
 
 // shared memory map (offsets from a 1024-aligned base)
 constexpr uint32_t OFF_UHI = 0;
@@ -56,7 +58,7 @@ constexpr uint32_t OFF_TMEM = OFF_BARS + 16 * 8;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_DYN = SMEM_USED + 1024;         // + alignment slack
 
-enum { BAR_FULL0 = 0, BAR_EMPTY0 = 2, BAR_UREADY = 4, BAR_ACC0 = 5 };   // indices into the mbarrier array
+enum { BAR_FULL0 = 0, BAR_EMPTY0 = 4, BAR_UREADY0 = 8, BAR_ACC0 = 12 };   // indices into the mbarrier array
 
 struct FusedParams {
   const uint8_t* tape;     // weight stages, SLOT bytes apart
@@ -204,8 +206,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
       mbar_init(&bars[BAR_FULL0 + s], 1);
       mbar_init(&bars[BAR_EMPTY0 + s], 1);
     }
-    mbar_init(&bars[BAR_UREADY], NT_EPI);
-    for (int m = 0; m < 4; ++m) mbar_init(&bars[BAR_ACC0 + m], 1);
+    for (int m = 0; m < 4; ++m) {
+      mbar_init(&bars[BAR_UREADY0 + m], 128);     // the 4 warps that own the channels of M-tile m
+      mbar_init(&bars[BAR_ACC0 + m], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
@@ -216,11 +220,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
   const uint32_t tmem = *tmem_slot;
   const int n_tiles = p.B;
 
-  if (warp == 16) {
+  if (warp >= 16) {
+   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+   if (warp == 16) {
     // ================= weight producer: walks the tape once per tile =====================
     if (lane == 0) {
       uint32_t it = 0;
-      const uint32_t wbytes = PRECISE ? 2 * W_HALF : W_HALF;
       auto push = [&](uint32_t stage, uint32_t bytes) {
         const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
         mbar_wait(&bars[BAR_EMPTY0 + slot], ph ^ 1);
@@ -228,106 +233,125 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
         bulk_g2s(sm + OFF_RING + slot * SLOT, p.tape + (size_t)stage * SLOT, bytes, &bars[BAR_FULL0 + slot]);
         ++it;
       };
+      auto push_pair = [&](uint32_t& st) {        // (hi, lo) images of one 128 x 64 weight block
+        push(st, W_HALF);
+        if (PRECISE) push(st + 1, W_HALF);
+        st += 2;
+      };
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t st = 0;
-        for (int i = 0; i < 4 * p.KIN; ++i) push(st++, wbytes);
+        for (int i = 0; i < 4 * p.KIN; ++i) push_pair(st);
         for (int l = 0; l < p.n_layers; ++l) {
-          push(st++, WBLK_BYTES);
-          if (PRECISE) push(st, WBLK_BYTES);
-          ++st;
-          for (int i = 0; i < 32; ++i) push(st++, wbytes);
+          push(st, WBLK_BLK);
+          push(st + 1, WBLK_BLK);
+          if (PRECISE) {
+            push(st + 2, WBLK_BLK);
+            push(st + 3, WBLK_BLK);
+          }
+          st += 4;
+          for (int i = 0; i < 32; ++i) push_pair(st);
         }
-        for (int i = 0; i < 8 * p.MH; ++i) push(st++, wbytes);
+        for (int i = 0; i < 8 * p.MH; ++i) push_pair(st);
       }
     }
-  } else if (warp == 17) {
+   } else if (warp == 17) {
     // ================= MMA issuer ==========================================================
     if (lane == 0) {
       uint32_t it = 0, uphase = 0;
       const uint32_t id_kk = idesc_bf16(128, NROW, 0, 0), id_mk = idesc_bf16(128, NROW, 1, 0);
       const uint32_t u_hi = smem_u32(sm + OFF_UHI), u_lo = smem_u32(sm + OFF_ULO), ring = smem_u32(sm + OFF_RING);
-      auto wait_u = [&]() {
-        mbar_wait(&bars[BAR_UREADY], uphase & 1);
+      auto wait_u_all = [&]() {       // whole operand tile published (K = all channels)
+        for (int m = 0; m < 4; ++m) mbar_wait(&bars[BAR_UREADY0 + m], uphase & 1);
         ++uphase;
         tc_fence_after_sync();
       };
-      // D[mt] (+)= W-stage[128 x 64] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
-      auto gemm_stage = [&](int mt, int kc, bool first) {
+      auto wait_stage = [&]() -> uint32_t {       // -> smem address of the next ring slot
         const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
         mbar_wait(&bars[BAR_FULL0 + slot], ph);
         tc_fence_after_sync();
-        const uint32_t wb = ring + slot * SLOT, d = tmem + (uint32_t)mt * NROW;
+        return ring + slot * SLOT;
+      };
+      auto release_stage = [&]() {
+        umma_commit(&bars[BAR_EMPTY0 + (it % NSLOT)]);
+        ++it;
+      };
+      // D[mt] (+)= W[128 x 64 block] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
+      auto gemm_pair = [&](int mt, int kc, bool first) {
+        const uint32_t d = tmem + (uint32_t)mt * NROW;
+        uint32_t wb = wait_stage();
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks) {
           const uint64_t a_hi = smem_desc(wb + ks * 32, 16, 1024, SWZ_128B);
-          const uint64_t b_hi = smem_desc(u_hi + kc * CBS + ks * 32, 16, 1024, SWZ_128B);
-          umma_bf16(d, a_hi, b_hi, id_kk, (first && ks == 0) ? 0u : 1u);
-          if (PRECISE) {
-            const uint64_t a_lo = smem_desc(wb + W_HALF + ks * 32, 16, 1024, SWZ_128B);
-            const uint64_t b_lo = smem_desc(u_lo + kc * CBS + ks * 32, 16, 1024, SWZ_128B);
-            umma_bf16(d, a_lo, b_hi, id_kk, 1u);
-            umma_bf16(d, a_hi, b_lo, id_kk, 1u);
-          }
+          umma_bf16(d, a_hi, smem_desc(u_hi + kc * CBS + ks * 32, 16, 1024, SWZ_128B), id_kk,
+                    (first && ks == 0) ? 0u : 1u);
+          if (PRECISE) umma_bf16(d, a_hi, smem_desc(u_lo + kc * CBS + ks * 32, 16, 1024, SWZ_128B), id_kk, 1u);
         }
-        umma_commit(&bars[BAR_EMPTY0 + slot]);
-        ++it;
-      };
-      auto signal_acc = [&]() {
-        for (int m = 0; m < 4; ++m) umma_commit(&bars[BAR_ACC0 + m]);
+        release_stage();
+        if (PRECISE) {
+          wb = wait_stage();
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_bf16(d, smem_desc(wb + ks * 32, 16, 1024, SWZ_128B),
+                      smem_desc(u_hi + kc * CBS + ks * 32, 16, 1024, SWZ_128B), id_kk, 1u);
+          release_stage();
+        }
       };
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // input projection
-        wait_u();
+        wait_u_all();
         for (int mt = 0; mt < 4; ++mt) {
-          for (int kc = 0; kc < p.KIN; ++kc) gemm_stage(mt, kc, kc == 0);
+          for (int kc = 0; kc < p.KIN; ++kc) gemm_pair(mt, kc, kc == 0);
           umma_commit(&bars[BAR_ACC0 + mt]);
         }
         for (int l = 0; l < p.n_layers; ++l) {
-          // token mix: D[mt][ch, row_out] = sum_row_in U^T[ch, row_in] * Wblk[row_out, row_in]
-          wait_u();
-          for (int half = 0; half < (PRECISE ? 2 : 1); ++half) {
-            const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
-            mbar_wait(&bars[BAR_FULL0 + slot], ph);
-            tc_fence_after_sync();
-            const uint32_t wb = ring + slot * SLOT;
-            for (uint32_t mt = 0; mt < 4; ++mt) {
-              const uint32_t d = tmem + mt * NROW;
-#pragma unroll
-              for (uint32_t ks = 0; ks < 5; ++ks) {
-                const uint64_t bd = smem_desc(wb + (ks >> 2) * WBLK_BLK + (ks & 3) * 32, 16, 1024, SWZ_128B);
-                const uint64_t a_hi = smem_desc(u_hi + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B);
-                if (half == 0) {
-                  umma_bf16(d, a_hi, bd, id_mk, ks == 0 ? 0u : 1u);
-                  if (PRECISE) {
-                    const uint64_t a_lo = smem_desc(u_lo + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B);
-                    umma_bf16(d, a_lo, bd, id_mk, 1u);
-                  }
-                } else {
-                  umma_bf16(d, a_hi, bd, id_mk, 1u);   // U_hi * Wblk_lo
-                }
-              }
-            }
-            umma_commit(&bars[BAR_EMPTY0 + slot]);
+          // token mix: D[mt][ch, row_out] = sum_row_in U^T[ch, row_in] * Wblk[row_out, row_in].
+          // Only the channels of M-tile mt are needed, so each M-tile starts as soon as ITS four
+          // epilogue warps have published (per-M-tile barrier) and overlaps the others' LayerNorm.
+          constexpr int NW = PRECISE ? 4 : 2;
+          uint32_t wb[4];
+          for (int i = 0; i < NW; ++i) {
+            wb[i] = wait_stage();
             ++it;
           }
-          signal_acc();
+          it -= NW;
+          for (uint32_t mt = 0; mt < 4; ++mt) {
+            mbar_wait(&bars[BAR_UREADY0 + mt], uphase & 1);
+            tc_fence_after_sync();
+            const uint32_t d = tmem + mt * NROW;
+#pragma unroll
+            for (uint32_t ks = 0; ks < 5; ++ks) {
+              const uint32_t boff = (ks & 3) * 32;
+              const uint64_t b_hi = smem_desc(wb[ks >> 2] + boff, 16, 1024, SWZ_128B);
+              const uint64_t a_hi = smem_desc(u_hi + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B);
+              umma_bf16(d, a_hi, b_hi, id_mk, ks == 0 ? 0u : 1u);
+              if (PRECISE) {
+                umma_bf16(d, smem_desc(u_lo + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B), b_hi, id_mk, 1u);
+                umma_bf16(d, a_hi, smem_desc(wb[2 + (ks >> 2)] + boff, 16, 1024, SWZ_128B), id_mk, 1u);
+              }
+            }
+            umma_commit(&bars[BAR_ACC0 + mt]);
+          }
+          ++uphase;
+          for (int i = 0; i < NW; ++i) release_stage();
           // channel mix
-          wait_u();
+          wait_u_all();
           for (int mt = 0; mt < 4; ++mt) {
-            for (int kc = 0; kc < 8; ++kc) gemm_stage(mt, kc, kc == 0);
+            for (int kc = 0; kc < 8; ++kc) gemm_pair(mt, kc, kc == 0);
             umma_commit(&bars[BAR_ACC0 + mt]);
           }
         }
         // output head (M-tiles beyond MH carry no work but still flip their barrier)
-        wait_u();
+        wait_u_all();
         for (int mt = 0; mt < 4; ++mt) {
           if (mt < p.MH)
-            for (int kc = 0; kc < 8; ++kc) gemm_stage(mt, kc, kc == 0);
+            for (int kc = 0; kc < 8; ++kc) gemm_pair(mt, kc, kc == 0);
           umma_commit(&bars[BAR_ACC0 + mt]);
         }
       }
     }
+   }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     // ================= epilogue: thread == channel ==========================================
     const int c = tid;
     const int mt = warp >> 2;
@@ -346,7 +370,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
     auto publish_u = [&]() {        // operand tile written (and accumulators consumed)
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&bars[BAR_UREADY]);
+      mbar_arrive(&bars[BAR_UREADY0 + mt]);
     };
     float h[72];
 
@@ -459,7 +483,8 @@ __global__ void build_w_stage_kernel(const float* __restrict__ src, int rows, in
   }
 }
 
-// token-mix stage pair: block-diagonal [80 x 128] (two passes share W_tok), K-major, hi stage then lo stage
+// token-mix stages: block-diagonal [80 x 128] (two passes share W_tok), K-major; one stage per
+// 64-wide k block: hi(k<64), hi(k>=64), lo(k<64), lo(k>=64)
 __global__ void build_wblk_kernel(const float* __restrict__ w_tok, int S, uint8_t* __restrict__ dst_hi,
                                   uint8_t* __restrict__ dst_lo) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NROW * 128; i += gridDim.x * blockDim.x) {
@@ -468,7 +493,7 @@ __global__ void build_wblk_kernel(const float* __restrict__ w_tok, int S, uint8_
     if (n < 2 * S && k < 2 * S && (n / S) == (k / S)) v = w_tok[(n % S) * S + (k % S)];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    const uint32_t off = (uint32_t)(k >> 6) * WBLK_BLK + tile_off(n, k & 63, 0);
+    const uint32_t off = (uint32_t)(k >> 6) * SLOT + tile_off(n, k & 63, 0);
     *reinterpret_cast<__nv_bfloat16*>(dst_hi + off) = hi;
     *reinterpret_cast<__nv_bfloat16*>(dst_lo + off) = lo;
   }
@@ -521,7 +546,7 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
       delete fs;
       return 1;
     }
-    fs->n_stages = 4 * fs->KIN + h->cfg.n_layers * 34 + 8 * fs->MH;
+    fs->n_stages = 8 * fs->KIN + h->cfg.n_layers * 68 + 16 * fs->MH;
     fs->tape_bytes = (size_t)fs->n_stages * SLOT;
     if (cudaMalloc(&fs->tape, fs->tape_bytes) != cudaSuccess) {
       delete fs;
@@ -541,26 +566,29 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
   const float* win = raw("input_mapping.weight");
   for (int mt = 0; mt < 4; ++mt)
     for (int kc = 0; kc < fs->KIN; ++kc) {
-      build_w_stage_kernel<<<16, 256, 0, s>>>(win, LS_D, h->JD, IN, mt * 128, kc * 64, fs->tape + st++ * SLOT);
+      build_w_stage_kernel<<<16, 256, 0, s>>>(win, LS_D, h->JD, IN, mt * 128, kc * 64, fs->tape + st * SLOT);
       LS_LAUNCH_CHECK(h);
+      st += 2;
     }
   for (int l = 0; l < h->cfg.n_layers; ++l) {
     const std::string p = "backbone.mlps." + std::to_string(l) + ".";
-    build_wblk_kernel<<<16, 256, 0, s>>>(raw(p + "block1.1.weight"), h->S, fs->tape + st * SLOT, fs->tape + (st + 1) * SLOT);
+    build_wblk_kernel<<<16, 256, 0, s>>>(raw(p + "block1.1.weight"), h->S, fs->tape + st * SLOT, fs->tape + (st + 2) * SLOT);
     LS_LAUNCH_CHECK(h);
-    st += 2;
+    st += 4;
     const float* wch = raw(p + "block2.1.weight");
     for (int mt = 0; mt < 4; ++mt)
       for (int kc = 0; kc < 8; ++kc) {
-        build_w_stage_kernel<<<16, 256, 0, s>>>(wch, LS_D, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st++ * SLOT);
+        build_w_stage_kernel<<<16, 256, 0, s>>>(wch, LS_D, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st * SLOT);
         LS_LAUNCH_CHECK(h);
+        st += 2;
       }
   }
   const float* wout = raw("output_process.poseFinal.weight");
   for (int mt = 0; mt < fs->MH; ++mt)
     for (int kc = 0; kc < 8; ++kc) {
-      build_w_stage_kernel<<<16, 256, 0, s>>>(wout, h->JD, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st++ * SLOT);
+      build_w_stage_kernel<<<16, 256, 0, s>>>(wout, h->JD, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st * SLOT);
       LS_LAUNCH_CHECK(h);
+      st += 2;
     }
   if ((int)st != fs->n_stages) return ls_fail(h, LS_EINVAL, "tape stage count mismatch");
   return LS_OK;
