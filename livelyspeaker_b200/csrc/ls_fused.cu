@@ -23,6 +23,7 @@
 // 17 MMA issuer + TMEM owner, 18-19 idle; warps 16-19 give most of their registers to the
 // epilogue warps with setmaxnreg so the 70-row residual stream fits without spilling.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "ls_internal.cuh"
 #include "ls_tc.cuh"
@@ -69,9 +70,11 @@ struct FusedParams {
   long long nsb, nsj, nsf;
   float* x_prev; float* pred_x0;
   ls_step_params sp;
+  long long* timing;       // debug (LS_FUSED_TIMING=1): clock64 stamps of block 0, threads 0 and 511
 };
 
-__device__ __forceinline__ float silu_fast(float z) { return z * __frcp_rn(1.f + __expf(-z)); }
+// x * sigmoid(x) with ex2.approx + rcp.approx (about 2 ulp; the IEEE reciprocal costs ~10 more instructions)
+__device__ __forceinline__ float silu_fast(float z) { return __fdividef(z, 1.f + __expf(-z)); }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
@@ -88,6 +91,28 @@ __device__ __forceinline__ void store_split(uint32_t u_s, uint32_t off, float v)
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     sts_u16(u_s + OFF_ULO + off, __bfloat16_as_ushort(lo));
   }
+}
+
+// Two values (rows n0, n1 of this thread's channel) -> bf16 hi (+ lo) with the packed converter
+// (F2FP, full-rate pipe; the scalar F2F conversion issues at MUFU rate and was the LayerNorm
+// store bottleneck).
+template <bool PRECISE>
+__device__ __forceinline__ void store_split2(uint32_t u_s, uint32_t off0, uint32_t off1, float v0, float v1) {
+  const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);      // .x = v0 (low half), .y = v1 (high half)
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi);
+  sts_u16(u_s + off0, (uint16_t)(hb & 0xFFFFu));
+  sts_u16(u_s + off1, (uint16_t)(hb >> 16));
+  if (PRECISE) {
+    const float r0 = v0 - __uint_as_float(hb << 16), r1 = v1 - __uint_as_float(hb & 0xFFFF0000u);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(r0, r1);
+    const uint32_t lb = *reinterpret_cast<const uint32_t*>(&lo);
+    sts_u16(u_s + OFF_ULO + off0, (uint16_t)(lb & 0xFFFFu));
+    sts_u16(u_s + OFF_ULO + off1, (uint16_t)(lb >> 16));
+  }
+}
+
+__device__ __forceinline__ uint32_t row_off(uint32_t pre_off, int n) {
+  return (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
 }
 
 // Per-row (sum, sum of squares) over the 512 channels -> stats[row] = (mean, 1/std).
@@ -157,12 +182,13 @@ template <int R, bool PRECISE>
 __device__ __forceinline__ void ln_store(const float (&h)[72], uint8_t* sm, uint32_t u_s, uint32_t pre_off, float alpha,
                                          float beta) {
   const float2* stats = reinterpret_cast<const float2*>(sm + OFF_STATS);
+  static_assert(R % 2 == 0, "rows are stored in pairs");
 #pragma unroll
-  for (int n = 0; n < R; ++n) {
-    const float2 st = stats[n];
-    const float u = fmaf((h[n] - st.x) * st.y, alpha, beta);
-    const uint32_t off = (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
-    store_split<PRECISE>(u_s, off, u);
+  for (int n = 0; n < R; n += 2) {
+    const float2 s0 = stats[n], s1 = stats[n + 1];
+    const float u0 = fmaf((h[n] - s0.x) * s0.y, alpha, beta);
+    const float u1 = fmaf((h[n + 1] - s1.x) * s1.y, alpha, beta);
+    store_split2<PRECISE>(u_s, row_off(pre_off, n), row_off(pre_off, n + 1), u0, u1);
   }
 }
 
@@ -190,7 +216,7 @@ __device__ __forceinline__ void for_acc(uint32_t taddr, F&& f) {
 }
 
 template <int S, bool PRECISE>
-__global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams p) {
   constexpr int R = 2 * S;            // real rows of a tile
   constexpr int NPRE = S - LS_F;      // prefix tokens per pass
   extern __shared__ uint8_t smem_raw[];
@@ -204,7 +230,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&bars[BAR_FULL0 + s], 1);
-      mbar_init(&bars[BAR_EMPTY0 + s], 1);
+      mbar_init(&bars[BAR_EMPTY0 + s], 2);        // the MMA issuers of BOTH CTAs of the pair release a slot
     }
     for (int m = 0; m < 4; ++m) {
       mbar_init(&bars[BAR_UREADY0 + m], 128);     // the 4 warps that own the channels of M-tile m
@@ -215,139 +241,156 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
   if (warp == 17) tmem_alloc<512>(tmem_slot);
   fence_proxy_async_smem();
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();             // barriers of both CTAs initialised before any multicast touches them
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const int n_tiles = p.B;
+  // The two CTAs of a cluster consume ONE weight stream (every stage is fetched half by each CTA and
+  // multicast to both), so they run the same number of rounds; a CTA without a real clip in the
+  // last round recomputes clip B-1 and writes nothing.
+  const int n_rounds = (p.B + (int)gridDim.x - 1) / (int)gridDim.x;
+  const uint32_t cta_rank = cluster_ctarank();
 
   if (warp >= 16) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
+   // Both single-thread roles address shared memory with 32-bit shared-space addresses only
+   // (32-register budget after setmaxnreg.dec).
+   const uint32_t bars_s = smem_u32(bars), ring_s = smem_u32(sm + OFF_RING);
+   const int n_layers = p.n_layers, KIN = p.KIN, MH = p.MH;
    if (warp == 16) {
-    // ================= weight producer: walks the tape once per tile =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      auto push = [&](uint32_t stage, uint32_t bytes) {
-        const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
-        mbar_wait(&bars[BAR_EMPTY0 + slot], ph ^ 1);
-        mbar_arrive_expect_tx(&bars[BAR_FULL0 + slot], bytes);
-        bulk_g2s(sm + OFF_RING + slot * SLOT, p.tape + (size_t)stage * SLOT, bytes, &bars[BAR_FULL0 + slot]);
-        ++it;
-      };
-      auto push_pair = [&](uint32_t& st) {        // (hi, lo) images of one 128 x 64 weight block
-        push(st, W_HALF);
-        if (PRECISE) push(st + 1, W_HALF);
-        st += 2;
-      };
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint32_t st = 0;
-        for (int i = 0; i < 4 * p.KIN; ++i) push_pair(st);
-        for (int l = 0; l < p.n_layers; ++l) {
-          push(st, WBLK_BLK);
-          push(st + 1, WBLK_BLK);
-          if (PRECISE) {
-            push(st + 2, WBLK_BLK);
-            push(st + 3, WBLK_BLK);
-          }
-          st += 4;
-          for (int i = 0; i < 32; ++i) push_pair(st);
+    // ================= weight producers ==================================================
+    // One thread sustains only ~1 bulk copy per 600 cycles whatever its size (bulk_bench.cu), so
+    // four lanes issue in parallel: lane j owns ring slot j, i.e. every 4th stage of the stream.
+    if (lane < NSLOT) {
+      const uint8_t* const tape = p.tape;
+      // stages consumed per round, in order: input projection | per layer: token-mix blocks,
+      // channel-mix blocks | head.  PRECISE walks every tape stage; the bf16 mode skips the lo images.
+      const uint32_t q_in = (PRECISE ? 8u : 4u) * (uint32_t)KIN, q_layer = PRECISE ? 68u : 34u;
+      const uint32_t q_round = q_in + q_layer * (uint32_t)n_layers + (PRECISE ? 16u : 8u) * (uint32_t)MH;
+      const uint32_t total = q_round * (uint32_t)n_rounds;
+      const uint32_t full_s = bars_s + 8 * (BAR_FULL0 + lane), empty_s = bars_s + 8 * (BAR_EMPTY0 + lane);
+      const uint32_t dst_s = ring_s + lane * SLOT;
+      for (uint32_t it = lane; it < total; it += NSLOT) {
+        const uint32_t q = it % q_round;
+        uint32_t stage, bytes = W_HALF;
+        if (PRECISE) {
+          stage = q;
+          if (q >= q_in && q < q_in + q_layer * (uint32_t)n_layers && (q - q_in) % 68u < 4u) bytes = WBLK_BLK;
+        } else if (q < q_in) {
+          stage = 2 * q;
+        } else if (q < q_in + q_layer * (uint32_t)n_layers) {
+          const uint32_t l = (q - q_in) / 34u, r = (q - q_in) % 34u;
+          stage = 8u * (uint32_t)KIN + 68u * l + (r < 2 ? r : 4u + 2u * (r - 2u));
+          if (r < 2) bytes = WBLK_BLK;
+        } else {
+          stage = 8u * (uint32_t)KIN + 68u * (uint32_t)n_layers + 2u * (q - q_in - 34u * (uint32_t)n_layers);
         }
-        for (int i = 0; i < 8 * p.MH; ++i) push_pair(st);
+        const uint32_t half = bytes >> 1;
+        mbar_wait_s(empty_s, ((it / NSLOT) & 1) ^ 1);                   // both CTAs are done with the slot
+        mbar_arrive_expect_tx_s(full_s, bytes);
+        bulk_g2s_mc_s(dst_s + cta_rank * half, tape + (size_t)stage * SLOT + cta_rank * half, half, full_s, (uint16_t)3);
       }
     }
    } else if (warp == 17) {
     // ================= MMA issuer ==========================================================
-    if (lane == 0) {
+    {   // all 32 lanes run this role in lock step; one elected lane issues (see ls_tc.cuh)
       uint32_t it = 0, uphase = 0;
-      const uint32_t id_kk = idesc_bf16(128, NROW, 0, 0), id_mk = idesc_bf16(128, NROW, 1, 0);
-      const uint32_t u_hi = smem_u32(sm + OFF_UHI), u_lo = smem_u32(sm + OFF_ULO), ring = smem_u32(sm + OFF_RING);
+      constexpr uint32_t id_kk = idesc_bf16(128, NROW, 0, 0), id_mk = idesc_bf16(128, NROW, 1, 0);
+      // Descriptor words: high word constant per layout, low word = (addr >> 4) | LBO field.
+      constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
+      const uint32_t u_s = smem_u32(sm + OFF_UHI);
+      const uint32_t uk = desc_lo32(u_s, 16);          // K-major view of U_hi   (U_lo = + U_BYTES/16)
+      const uint32_t um = desc_lo32(u_s, CBS);         // MN-major view of U_hi
+      constexpr uint32_t LO = U_BYTES >> 4;            // descriptor-address distance U_hi -> U_lo
+      long long t_full = 0, t_u = 0, n_full = 0;
+      const bool dbg_t = p.timing != nullptr && blockIdx.x == 0 && lane == 0;
       auto wait_u_all = [&]() {       // whole operand tile published (K = all channels)
-        for (int m = 0; m < 4; ++m) mbar_wait(&bars[BAR_UREADY0 + m], uphase & 1);
+        const long long c0 = dbg_t ? clock64() : 0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + m), uphase & 1);
+        if (dbg_t) t_u += clock64() - c0;
         ++uphase;
         tc_fence_after_sync();
       };
-      auto wait_stage = [&]() -> uint32_t {       // -> smem address of the next ring slot
+      auto wait_stage = [&]() -> uint32_t {       // -> descriptor low word of the next ring slot
         const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
-        mbar_wait(&bars[BAR_FULL0 + slot], ph);
+        const long long c0 = dbg_t ? clock64() : 0;
+        mbar_wait_s(bars_s + 8 * (BAR_FULL0 + slot), ph);
+        if (dbg_t) { t_full += clock64() - c0; ++n_full; }
         tc_fence_after_sync();
-        return ring + slot * SLOT;
+        return desc_lo32(ring_s + slot * SLOT, 16);
       };
       auto release_stage = [&]() {
-        umma_commit(&bars[BAR_EMPTY0 + (it % NSLOT)]);
+        umma_commit_mc_s_elect(bars_s + 8 * (BAR_EMPTY0 + (it % NSLOT)), (uint16_t)3);
         ++it;
       };
       // D[mt] (+)= W[128 x 64 block] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
-      auto gemm_pair = [&](int mt, int kc, bool first) {
-        const uint32_t d = tmem + (uint32_t)mt * NROW;
-        uint32_t wb = wait_stage();
+      auto gemm_pair = [&](uint32_t d, uint32_t ub, bool first) {
+        uint32_t wl = wait_stage();
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks) {
-          const uint64_t a_hi = smem_desc(wb + ks * 32, 16, 1024, SWZ_128B);
-          umma_bf16(d, a_hi, smem_desc(u_hi + kc * CBS + ks * 32, 16, 1024, SWZ_128B), id_kk,
-                    (first && ks == 0) ? 0u : 1u);
-          if (PRECISE) umma_bf16(d, a_hi, smem_desc(u_lo + kc * CBS + ks * 32, 16, 1024, SWZ_128B), id_kk, 1u);
+          umma_bf16_split_elect(d, wl + 2 * ks, DH, ub + 2 * ks, DH, id_kk, (first && ks == 0) ? 0u : 1u);
+          if (PRECISE) umma_bf16_split_elect(d, wl + 2 * ks, DH, ub + LO + 2 * ks, DH, id_kk, 1u);
         }
         release_stage();
         if (PRECISE) {
-          wb = wait_stage();
+          wl = wait_stage();
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_bf16(d, smem_desc(wb + ks * 32, 16, 1024, SWZ_128B),
-                      smem_desc(u_hi + kc * CBS + ks * 32, 16, 1024, SWZ_128B), id_kk, 1u);
+          for (uint32_t ks = 0; ks < 4; ++ks) umma_bf16_split_elect(d, wl + 2 * ks, DH, ub + 2 * ks, DH, id_kk, 1u);
           release_stage();
         }
       };
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // input projection
+      // one full GEMM over all of U: n_mt M-tiles x n_kc 64-channel blocks
+      auto gemm_all = [&](int n_mt, int n_kc) {
         wait_u_all();
+#pragma unroll 1
         for (int mt = 0; mt < 4; ++mt) {
-          for (int kc = 0; kc < p.KIN; ++kc) gemm_pair(mt, kc, kc == 0);
-          umma_commit(&bars[BAR_ACC0 + mt]);
+          if (mt < n_mt)
+#pragma unroll 1
+            for (int kc = 0; kc < n_kc; ++kc) gemm_pair(tmem + (uint32_t)mt * NROW, uk + (uint32_t)kc * (CBS >> 4), kc == 0);
+          umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));    // M-tiles without work still flip their barrier
         }
-        for (int l = 0; l < p.n_layers; ++l) {
+      };
+#pragma unroll 1
+      for (int round = 0; round < n_rounds; ++round) {
+        gemm_all(4, KIN);                                  // input projection
+#pragma unroll 1
+        for (int l = 0; l < n_layers; ++l) {
           // token mix: D[mt][ch, row_out] = sum_row_in U^T[ch, row_in] * Wblk[row_out, row_in].
           // Only the channels of M-tile mt are needed, so each M-tile starts as soon as ITS four
           // epilogue warps have published (per-M-tile barrier) and overlaps the others' LayerNorm.
           constexpr int NW = PRECISE ? 4 : 2;
-          uint32_t wb[4];
+          uint32_t wl[NW];
+#pragma unroll
           for (int i = 0; i < NW; ++i) {
-            wb[i] = wait_stage();
+            wl[i] = wait_stage();
             ++it;
           }
           it -= NW;
+#pragma unroll 1
           for (uint32_t mt = 0; mt < 4; ++mt) {
-            mbar_wait(&bars[BAR_UREADY0 + mt], uphase & 1);
+            mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + mt), uphase & 1);
             tc_fence_after_sync();
             const uint32_t d = tmem + mt * NROW;
+            const uint32_t ua = um + 2 * mt * (CBS >> 4);
 #pragma unroll
             for (uint32_t ks = 0; ks < 5; ++ks) {
-              const uint32_t boff = (ks & 3) * 32;
-              const uint64_t b_hi = smem_desc(wb[ks >> 2] + boff, 16, 1024, SWZ_128B);
-              const uint64_t a_hi = smem_desc(u_hi + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B);
-              umma_bf16(d, a_hi, b_hi, id_mk, ks == 0 ? 0u : 1u);
+              const uint32_t bw = wl[ks >> 2] + 2 * (ks & 3), ao = ua + ks * (2048 >> 4);
+              umma_bf16_split_elect(d, ao, DH, bw, DH, id_mk, ks == 0 ? 0u : 1u);
               if (PRECISE) {
-                umma_bf16(d, smem_desc(u_lo + 2 * mt * CBS + ks * 2048, CBS, 1024, SWZ_128B), b_hi, id_mk, 1u);
-                umma_bf16(d, a_hi, smem_desc(wb[2 + (ks >> 2)] + boff, 16, 1024, SWZ_128B), id_mk, 1u);
+                umma_bf16_split_elect(d, ao + LO, DH, bw, DH, id_mk, 1u);
+                umma_bf16_split_elect(d, ao, DH, wl[NW - 2 + (ks >> 2)] + 2 * (ks & 3), DH, id_mk, 1u);
               }
             }
-            umma_commit(&bars[BAR_ACC0 + mt]);
+            umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));
           }
           ++uphase;
+#pragma unroll
           for (int i = 0; i < NW; ++i) release_stage();
-          // channel mix
-          wait_u_all();
-          for (int mt = 0; mt < 4; ++mt) {
-            for (int kc = 0; kc < 8; ++kc) gemm_pair(mt, kc, kc == 0);
-            umma_commit(&bars[BAR_ACC0 + mt]);
-          }
+          gemm_all(4, 8);                                  // channel mix
         }
-        // output head (M-tiles beyond MH carry no work but still flip their barrier)
-        wait_u_all();
-        for (int mt = 0; mt < 4; ++mt) {
-          if (mt < p.MH)
-            for (int kc = 0; kc < 8; ++kc) gemm_pair(mt, kc, kc == 0);
-          umma_commit(&bars[BAR_ACC0 + mt]);
-        }
+        gemm_all(MH, 8);                                   // output head
       }
+      if (dbg_t) { p.timing[500] = t_full; p.timing[501] = t_u; p.timing[502] = n_full; }
     }
    }
   } else {
@@ -373,8 +416,16 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
       mbar_arrive(&bars[BAR_UREADY0 + mt]);
     };
     float h[72];
+    int tix = 0;
+    auto stamp = [&]() {
+      if (p.timing != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 511) && tix < 256)
+        p.timing[(tid ? 256 : 0) + tix++] = clock64();
+    };
 
-    for (int b = blockIdx.x; b < n_tiles; b += gridDim.x) {
+    for (int round = 0; round < n_rounds; ++round) {
+      const int b_raw = (int)blockIdx.x + round * (int)gridDim.x;
+      const bool valid = b_raw < p.B;
+      const int b = valid ? b_raw : p.B - 1;
       // ---- X operand: x_t[b] (hi, lo) into rows p*S + NPRE + f, k = j ----------------------
       const float* xb = p.x_t + (size_t)b * p.JD * LS_F;
       for (int i = tid; i < p.JD * LS_F; i += NT_EPI) {
@@ -384,6 +435,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
         store_split<PRECISE>(u_s, tile_off(S + NPRE + f, j, CBS), v);
       }
       publish_u();
+      stamp();   // 0: X operand published
       // ---- residual stream init: hoisted terms now, projection result when it lands --------
       {
         const float mu = p.z_mu[(size_t)b * LS_D + c], sd = __expf(0.5f * p.z_lv[(size_t)b * LS_D + c]);
@@ -403,6 +455,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
       for_acc<R>(lane_taddr, [&](int n, float v) {
         if ((n % S) >= NPRE) h[n] += v;          // prefix-token rows keep their direct values
       });
+      stamp();   // 1: input projection consumed
 
       for (int l = 0; l < p.n_layers; ++l) {
         const LsLayerW L = p.w.layer[l];
@@ -413,17 +466,25 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
         for (int n = 0; n < R; ++n) h[n] += emb;
         if (l == 0) ln_stats<R>(h, sm, false);     // provisional means for the shift
         ln_stats<R>(h, sm, true);
+        stamp();   // LN1 stats done
         ln_store<R, PRECISE>(h, sm, u_s, pre_off, a1, b1);
         publish_u();
+        stamp();   // U1 published
         // token mix epilogue: x = x + silu(conv + bias)
         wait_acc();
+        stamp();   // token-mix accumulator ready
         for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(v + btok_s[n]); });
+        stamp();   // token-mix epilogue done
         ln_stats<R>(h, sm, true);
+        stamp();   // LN2 stats done
         ln_store<R, PRECISE>(h, sm, u_s, pre_off, a2, b2);
         publish_u();
+        stamp();   // U2 published
         // channel mix epilogue: x = x + silu(linear + bias)
         wait_acc();
+        stamp();   // channel-mix accumulator ready
         for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(v + bch); });
+        stamp();   // channel-mix epilogue done
       }
 
       // ---- output head operand: plain hi/lo split of h -------------------------------------
@@ -431,16 +492,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
       // MMAs of the other M-tiles still read U until their own accumulator barrier fires.
       epi_bar();
 #pragma unroll
-      for (int n = 0; n < R; ++n) {
-        const uint32_t off = (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
-        store_split<PRECISE>(u_s, off, h[n]);
-      }
+      for (int n = 0; n < R; n += 2)
+        store_split2<PRECISE>(u_s, row_off(pre_off, n), row_off(pre_off, n + 1), h[n], h[n + 1]);
       publish_u();
       wait_acc();
       if (warp * 32 < p.JD) {                    // warp-uniform: tcgen05.ld is .aligned
         // h is dead: reuse it for the head outputs (lane = output feature j, column = row)
         for_acc<R>(lane_taddr, [&](int n, float v) { h[n] = v; });
-        if (c < p.JD) {
+        if (c < p.JD && valid) {
           const float bo = p.w.b_out[c], sc = p.scale[b];
           const size_t base = ((size_t)b * p.JD + c) * LS_F;
           const float* nzp = p.noise ? p.noise + (size_t)b * p.nsb + (size_t)c * p.nsj : nullptr;
@@ -464,7 +523,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams
   }
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before_sync();
-  __syncthreads();
+  cluster_sync_all();             // the peer may still multicast commits into this CTA's barriers
   if (warp == 17) tmem_dealloc<512>(tmem);
 }
 
@@ -514,7 +573,8 @@ int launch_fused(ls_handle* h, FusedState* fs, const FusedParams& fp, cudaStream
     LS_CUDA(h, cudaFuncSetAttribute(fused_step_kernel<S, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN));
     done = true;
   }
-  const int grid = fp.B < fs->sm_count ? fp.B : fs->sm_count;
+  // clusters of 2: an even grid, at most one CTA per SM
+  const int grid = (fp.B + 1 < fs->sm_count ? fp.B + 1 : fs->sm_count) & ~1;
   fused_step_kernel<S, PRECISE><<<grid, NT_ALL, SMEM_DYN, s>>>(fp);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
@@ -614,6 +674,34 @@ int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const fl
   fp.nsb = sb; fp.nsj = sj; fp.nsf = sf;
   fp.x_prev = x_prev; fp.pred_x0 = pred_x0;
   fp.sp = *p;
-  if (h->S == 35) return precise ? launch_fused<35, true>(h, fs, fp, s) : launch_fused<35, false>(h, fs, fp, s);
-  return precise ? launch_fused<36, true>(h, fs, fp, s) : launch_fused<36, false>(h, fs, fp, s);
+  fp.timing = nullptr;
+  static long long* tbuf = nullptr;
+  const bool timing = getenv("LS_FUSED_TIMING") != nullptr;
+  if (timing) {
+    if (!tbuf) cudaMalloc(&tbuf, 512 * sizeof(long long));
+    cudaMemsetAsync(tbuf, 0, 512 * sizeof(long long), s);
+    fp.timing = tbuf;
+  }
+  int rc;
+  if (h->S == 35) rc = precise ? launch_fused<35, true>(h, fs, fp, s) : launch_fused<35, false>(h, fs, fp, s);
+  else rc = precise ? launch_fused<36, true>(h, fs, fp, s) : launch_fused<36, false>(h, fs, fp, s);
+  if (timing && rc == LS_OK) {
+    long long t[512];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(t, tbuf, sizeof(t), cudaMemcpyDeviceToHost);
+    static const char* names[] = {"LN1 stats", "U1 publish", "tok acc wait", "tok epilogue", "LN2 stats", "U2 publish",
+                                  "ch acc wait", "ch epilogue"};
+    fprintf(stderr, "[fused timing] MMA thread: waited %lld cyc on %lld weight stages (%.0f each), %lld cyc on operand tiles\n",
+            t[500], t[502], t[502] ? (double)t[500] / t[502] : 0.0, t[501]);
+    for (int w = 0; w < 2; ++w) {
+      const long long* q = t + 256 * w;
+      fprintf(stderr, "[fused timing] thread %d: X publish -> in-proj consumed %lld cyc\n", w ? 511 : 0, q[1] - q[0]);
+      for (int l = 0; l < h->cfg.n_layers && 2 + 8 * l + 7 < 256; ++l) {
+        fprintf(stderr, "  layer %d:", l);
+        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %lld |", names[k], q[2 + 8 * l + k] - q[1 + 8 * l + k]);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
+  return rc;
 }

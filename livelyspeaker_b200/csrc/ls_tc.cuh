@@ -11,6 +11,10 @@ namespace lstc {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- mbarrier ------------------------------------------------------------------------
+// try_wait is given a suspend-time hint so a waiting thread SLEEPS in hardware until the phase
+// completes instead of spinning: 16 epilogue warps polling without it took the issue slots the
+// single MMA-issuing thread needs (measured ~100 cycles per tcgen05.mma issue instead of ~52).
+constexpr uint32_t MBAR_SUSPEND_HINT = 0x989680u;
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -25,16 +29,70 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_HINT)
       : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
+}
+
+// shared-space (32-bit) address variants: the single-thread producer / MMA roles run on a
+// 32-register budget, where 64-bit generic pointers and their cvta conversions cause spills.
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(bar_s), "r"(parity), "r"(MBAR_SUSPEND_HINT)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_s(uint32_t bar_s, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst_s, const void* gmem_src, uint32_t bytes, uint32_t bar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+               "l"(gmem_src), "r"(bytes), "r"(bar_s)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit_s(uint32_t bar_s) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s) : "memory");
+}
+
+// ---- thread-block clusters: weight stages are multicast to both CTAs of a pair ------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of all CTAs in the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy whose destination (same CTA-relative offset) and mbarrier signal are replicated in
+// every CTA of `mask`
+__device__ __forceinline__ void bulk_g2s_mc_s(uint32_t dst_s, const void* gmem_src, uint32_t bytes, uint32_t bar_s,
+                                              uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          dst_s),
+      "l"(gmem_src), "r"(bytes), "r"(bar_s), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc_s(uint32_t bar_s, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   bar_s),
+               "h"(mask)
+               : "memory");
 }
 
 // ---- proxies / fences ------------------------------------------------------------------
@@ -122,6 +180,60 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, with each descriptor passed as (low word, high word).  For a fixed layout the high word
+// (SBO, version, swizzle) is a constant and the low word is (address >> 4) | (LBO >> 4) << 16, so
+// the issuing thread steps through K with one 32-bit add per operand.
+__device__ __forceinline__ void umma_bf16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-collective forms: executed by ALL 32 lanes of the MMA warp in uniform control flow, one
+// elected lane issues.  This is what lets ptxas keep descriptors in uniform registers; issuing from
+// inside an `if (lane == 0)` region instead wraps every UTCHMMA in an R2UR/ELECT/BRA.U.ANY
+// uniformisation loop (measured ~100 instead of ~52 cycles per MMA).
+__device__ __forceinline__ void umma_bf16_split_elect(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                      uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_s_elect(uint32_t bar_s) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_s)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_s_elect(uint32_t bar_s, uint16_t mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          bar_s),
+      "h"(mask)
+      : "memory");
+}
+
+__host__ __device__ constexpr uint32_t desc_hi32(uint32_t sbo_bytes, uint32_t swz) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (swz << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo32(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+
 // mbarrier arrives once all previously issued MMAs of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
