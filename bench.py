@@ -37,6 +37,15 @@ def model_args(dims):
                                  njoints=dims.njoints)
 
 
+def ncu_traffic(kernel_impl, dataset, batch):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None
+    when the capture is for another kernel / workload.  Never measured live: a run under ncu is not a bench."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if kernel_impl == "tc_bf16x3" and dataset == "ted" and batch == 512 and os.path.exists(p):
+        return json.load(open(p)).get("dram_bytes_per_launch")
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -311,7 +320,7 @@ def main():
             "gpu_launches": launches,
             "launches_per_step": launches_per_step,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(impl, a.dataset, B), "peak_source": peak_src,
                          "kernel_ms": kern_ms, "flop_per_launch": flop_step,
                          "note": "algorithmic flops (BASELINE.md section 3): x3 of the bf16x3 split and padding not counted"},
             "clocks": clk,
