@@ -134,14 +134,15 @@ def run_reference_arm(a, dims, rank):
     value, per_step = cpu_port_steps_per_s(dims, a.batch, n_steps, max(1, min(a.warmup, 1)), sample_batch, threads)
     sample = "%d oracle p_sample steps at B=%d clips (CFG on), %.3f s each, scaled to B=%d" % (
         n_steps, sample_batch, per_step, a.batch)
-    line = {"impl": "reference", "metric": "denoising-steps/sec", "value": value * a.gpus,
+    # the unit (steps of 512 clips) does not depend on N: the host cores do not scale with --gpus
+    line = {"impl": "reference", "metric": "denoising-steps/sec", "value": value,
             "unit": "steps/s (1 step = %d clips advanced one timestep, CFG on)" % a.batch, "n_gpus": a.gpus,
             "steps": n_steps, "warmup": 1, "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, dims),
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value * a.gpus, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "clips_per_s": value * a.gpus * a.batch / T_FULL}
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "clips_per_s": value * a.batch / T_FULL}
     print(json.dumps(line), flush=True)
 
 

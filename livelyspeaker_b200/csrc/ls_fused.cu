@@ -43,6 +43,9 @@ constexpr uint32_t CBS = RGS * 1024;           // bytes between 64-channel block
 constexpr uint32_t U_BYTES = 8 * CBS;          // one of U_hi / U_lo
 constexpr uint32_t SLOT = 16384;               // ring slot = tape stage pitch
 constexpr int NSLOT = 4;
+#ifndef LS_MULTICAST
+#define LS_MULTICAST 1   // 1: weight stages fetched half by each CTA of the pair and multicast to both
+#endif
 constexpr uint32_t W_HALF = 16384;             // 128 x 64 bf16 weight block (hi or lo) = one stage
 constexpr uint32_t WBLK_BLK = 10 * 1024;       // token-mix weights: 80 rows x 64 k = one stage
 
@@ -160,7 +163,7 @@ __device__ __forceinline__ void ln_stats(const float (&h)[72], uint8_t* sm, bool
     }
   }
   epi_bar();
-  if (tid < R) {
+  if (tid < R) {              // 70 threads in parallel, 16 pipelined loads each (a warp-shuffle finish was slower)
     float ss = 0.f, qq = 0.f;
 #pragma unroll
     for (int w = 0; w < 16; ++w) {
@@ -215,10 +218,17 @@ __device__ __forceinline__ void for_acc(uint32_t taddr, F&& f) {
   }
 }
 
+// Token-mix bias through the GEMM: when the 72-row tile has a spare row (TED: 2S = 70), that row of
+// U holds 1.0 and column 2S of the block-diagonal weight holds the bias, so the epilogue needs no
+// per-row bias load.  BEAT (2S = 72) has no spare row and adds the bias from shared memory.
+template <int S>
+struct TokBias { static constexpr bool kInGemm = (2 * S + 1 <= 72); };
+
 template <int S, bool PRECISE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams p) {
   constexpr int R = 2 * S;            // real rows of a tile
   constexpr int NPRE = S - LS_F;      // prefix tokens per pass
+  static_assert(R <= 72, "tile rows");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BARS);
@@ -230,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       mbar_init(&bars[BAR_FULL0 + s], 1);
-      mbar_init(&bars[BAR_EMPTY0 + s], 2);        // the MMA issuers of BOTH CTAs of the pair release a slot
+      mbar_init(&bars[BAR_EMPTY0 + s], LS_MULTICAST ? 2 : 1);   // multicast: the MMA issuers of BOTH CTAs release a slot
     }
     for (int m = 0; m < 4; ++m) {
       mbar_init(&bars[BAR_UREADY0 + m], 128);     // the 4 warps that own the channels of M-tile m
@@ -239,6 +249,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
     mbar_fence_init();
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
+  __syncthreads();
+  if (TokBias<S>::kInGemm && tid < LS_D)          // the ones row (hi = 1.0, lo = 0) - never overwritten
+    sts_u16(smem_u32(sm + OFF_UHI) + tile_off(R, tid, CBS), (uint16_t)0x3F80u);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   cluster_sync_all();             // barriers of both CTAs initialised before any multicast touches them
@@ -284,10 +297,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         } else {
           stage = 8u * (uint32_t)KIN + 68u * (uint32_t)n_layers + 2u * (q - q_in - 34u * (uint32_t)n_layers);
         }
-        const uint32_t half = bytes >> 1;
-        mbar_wait_s(empty_s, ((it / NSLOT) & 1) ^ 1);                   // both CTAs are done with the slot
+        mbar_wait_s(empty_s, ((it / NSLOT) & 1) ^ 1);                   // (both CTAs are) done with the slot
         mbar_arrive_expect_tx_s(full_s, bytes);
+#if LS_MULTICAST
+        const uint32_t half = bytes >> 1;
         bulk_g2s_mc_s(dst_s + cta_rank * half, tape + (size_t)stage * SLOT + cta_rank * half, half, full_s, (uint16_t)3);
+#else
+        bulk_g2s_s(dst_s, tape + (size_t)stage * SLOT, bytes, full_s);
+#endif
       }
     }
    } else if (warp == 17) {
@@ -320,7 +337,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         return desc_lo32(ring_s + slot * SLOT, 16);
       };
       auto release_stage = [&]() {
+#if LS_MULTICAST
         umma_commit_mc_s_elect(bars_s + 8 * (BAR_EMPTY0 + (it % NSLOT)), (uint16_t)3);
+#else
+        umma_commit_s_elect(bars_s + 8 * (BAR_EMPTY0 + (it % NSLOT)));
+#endif
         ++it;
       };
       // D[mt] (+)= W[128 x 64 block] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
@@ -473,7 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         // token mix epilogue: x = x + silu(conv + bias)
         wait_acc();
         stamp();   // token-mix accumulator ready
-        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(v + btok_s[n]); });
+        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[n]); });
         stamp();   // token-mix epilogue done
         ln_stats<R>(h, sm, true);
         stamp();   // LN2 stats done
@@ -544,12 +565,14 @@ __global__ void build_w_stage_kernel(const float* __restrict__ src, int rows, in
 
 // token-mix stages: block-diagonal [80 x 128] (two passes share W_tok), K-major; one stage per
 // 64-wide k block: hi(k<64), hi(k>=64), lo(k<64), lo(k>=64)
-__global__ void build_wblk_kernel(const float* __restrict__ w_tok, int S, uint8_t* __restrict__ dst_hi,
-                                  uint8_t* __restrict__ dst_lo) {
+__global__ void build_wblk_kernel(const float* __restrict__ w_tok, const float* __restrict__ b_tok, int S,
+                                  uint8_t* __restrict__ dst_hi, uint8_t* __restrict__ dst_lo) {
+  const bool bias_col = (2 * S + 1 <= 72);         // must match TokBias<S>::kInGemm
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NROW * 128; i += gridDim.x * blockDim.x) {
     const int n = i >> 7, k = i & 127;
     float v = 0.f;
     if (n < 2 * S && k < 2 * S && (n / S) == (k / S)) v = w_tok[(n % S) * S + (k % S)];
+    if (bias_col && n < 2 * S && k == 2 * S) v = b_tok[n % S];
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const uint32_t off = (uint32_t)(k >> 6) * SLOT + tile_off(n, k & 63, 0);
@@ -632,7 +655,8 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
     }
   for (int l = 0; l < h->cfg.n_layers; ++l) {
     const std::string p = "backbone.mlps." + std::to_string(l) + ".";
-    build_wblk_kernel<<<16, 256, 0, s>>>(raw(p + "block1.1.weight"), h->S, fs->tape + st * SLOT, fs->tape + (st + 2) * SLOT);
+    build_wblk_kernel<<<16, 256, 0, s>>>(raw(p + "block1.1.weight"), raw(p + "block1.1.bias"), h->S, fs->tape + st * SLOT,
+                                         fs->tape + (st + 2) * SLOT);
     LS_LAUNCH_CHECK(h);
     st += 4;
     const float* wch = raw(p + "block2.1.weight");
