@@ -311,6 +311,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
     // ================= MMA issuer ==========================================================
     {   // all 32 lanes run this role in lock step; one elected lane issues (see ls_tc.cuh)
       uint32_t it = 0, uphase = 0;
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);    // provably warp-uniform copy
       constexpr uint32_t id_kk = idesc_bf16(128, NROW, 0, 0), id_mk = idesc_bf16(128, NROW, 1, 0);
       // Descriptor words: high word constant per layout, low word = (addr >> 4) | LBO field.
       constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
@@ -318,21 +319,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       const uint32_t uk = desc_lo32(u_s, 16);          // K-major view of U_hi   (U_lo = + U_BYTES/16)
       const uint32_t um = desc_lo32(u_s, CBS);         // MN-major view of U_hi
       constexpr uint32_t LO = U_BYTES >> 4;            // descriptor-address distance U_hi -> U_lo
-      long long t_full = 0, t_u = 0, n_full = 0;
-      const bool dbg_t = p.timing != nullptr && blockIdx.x == 0 && lane == 0;
       auto wait_u_all = [&]() {       // whole operand tile published (K = all channels)
-        const long long c0 = dbg_t ? clock64() : 0;
 #pragma unroll
         for (int m = 0; m < 4; ++m) mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + m), uphase & 1);
-        if (dbg_t) t_u += clock64() - c0;
         ++uphase;
         tc_fence_after_sync();
       };
       auto wait_stage = [&]() -> uint32_t {       // -> descriptor low word of the next ring slot
         const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
-        const long long c0 = dbg_t ? clock64() : 0;
         mbar_wait_s(bars_s + 8 * (BAR_FULL0 + slot), ph);
-        if (dbg_t) { t_full += clock64() - c0; ++n_full; }
         tc_fence_after_sync();
         return desc_lo32(ring_s + slot * SLOT, 16);
       };
@@ -367,7 +362,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         for (int mt = 0; mt < 4; ++mt) {
           if (mt < n_mt)
 #pragma unroll 1
-            for (int kc = 0; kc < n_kc; ++kc) gemm_pair(tmem + (uint32_t)mt * NROW, uk + (uint32_t)kc * (CBS >> 4), kc == 0);
+            for (int kc = 0; kc < n_kc; ++kc) gemm_pair(tmem_u + (uint32_t)mt * NROW, uk + (uint32_t)kc * (CBS >> 4), kc == 0);
           umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));    // M-tiles without work still flip their barrier
         }
       };
@@ -391,7 +386,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           for (uint32_t mt = 0; mt < 4; ++mt) {
             mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + mt), uphase & 1);
             tc_fence_after_sync();
-            const uint32_t d = tmem + mt * NROW;
+            const uint32_t d = tmem_u + mt * NROW;
             const uint32_t ua = um + 2 * mt * (CBS >> 4);
 #pragma unroll
             for (uint32_t ks = 0; ks < 5; ++ks) {
@@ -411,7 +406,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         }
         gemm_all(MH, 8);                                   // output head
       }
-      if (dbg_t) { p.timing[500] = t_full; p.timing[501] = t_u; p.timing[502] = n_full; }
     }
    }
   } else {
@@ -715,8 +709,6 @@ int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const fl
     cudaMemcpy(t, tbuf, sizeof(t), cudaMemcpyDeviceToHost);
     static const char* names[] = {"LN1 stats", "U1 publish", "tok acc wait", "tok epilogue", "LN2 stats", "U2 publish",
                                   "ch acc wait", "ch epilogue"};
-    fprintf(stderr, "[fused timing] MMA thread: waited %lld cyc on %lld weight stages (%.0f each), %lld cyc on operand tiles\n",
-            t[500], t[502], t[502] ? (double)t[500] / t[502] : 0.0, t[501]);
     for (int w = 0; w < 2; ++w) {
       const long long* q = t + 256 * w;
       fprintf(stderr, "[fused timing] thread %d: X publish -> in-proj consumed %lld cyc\n", w ? 511 : 0, q[1] - q[0]);
