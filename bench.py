@@ -37,12 +37,14 @@ def model_args(dims):
                                  njoints=dims.njoints)
 
 
-def ncu_traffic(kernel_impl, dataset, batch):
+def ncu_traffic(kernel_impl, dataset, batch, steps_per_launch):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None
     when the capture is for another kernel / workload.  Never measured live: a run under ncu is not a bench."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if kernel_impl == "tc_bf16x3" and dataset == "ted" and batch == 512 and os.path.exists(p):
-        return json.load(open(p)).get("dram_bytes_per_launch")
+        d = json.load(open(p))
+        if d.get("steps_per_launch", 1) == steps_per_launch:
+            return d.get("dram_bytes_per_launch")
     return None
 
 
@@ -151,7 +153,8 @@ def workload_config(a, dims):
                         % (a.batch, dims.jd, T_FULL) if dims.dataset == "ted" else
                         "BEAT RAG sampling B=%d/GPU, F=34, J*D=%d, T=%d ancestral" % (a.batch, dims.jd, T_FULL),
             "global_batch": a.batch * a.gpus, "timesteps": T_FULL, "sampler": a.sampler,
-            "l2": "flushed between timed steps (256 MiB memset outside the event bracket)",
+            "l2": "flushed between timed launches of %d steps (256 MiB memset outside the event bracket)" % a.chunk,
+            "steps_per_launch": a.chunk,
             "parallelism": "batch shard x%d, no per-step collective, 1 all_gather at loop end" % a.gpus}
 
 
@@ -165,6 +168,7 @@ def main():
     ap.add_argument("--dataset", default="ted", choices=["ted", "beat"])
     ap.add_argument("--batch", type=int, default=512, help="clips per GPU")
     ap.add_argument("--sampler", default="ancestral", choices=["ancestral", "ddim"])
+    ap.add_argument("--chunk", type=int, default=16, help="loop iterations per launch (ls_step_multi), 1..16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
@@ -222,56 +226,72 @@ def main():
     idx = [T_FULL - 1 - (k % T_FULL) for k in range(W + K)]
     params = [diffusion.step_params(i, ddim=ddim, eta=0.0, clip_denoised=False) for i in idx]
 
-    def one_step(k, x_in):
-        e_c = torch.randn(B, 1, 512, device=dev)
-        e_u = torch.randn(B, 1, 512, device=dev)
-        nz = torch.randn_like(perm_like)
-        x_out = torch.empty_like(x_in)
-        eng.step(params[k], x_in, e_c, e_u, nz, scale, x_out, None)
-        return x_out
+    C = max(1, min(a.chunk, ls.MAX_FUSED_STEPS))
 
-    for k in range(W):
-        x = one_step(k, x)
+    def run_chunk(k0, n, x_in):
+        """n consecutive loop iterations as p_sample_loop runs them on the fused route: the reference's
+        per-step draws (3 torch RNG launches per step), then ONE ls_step_multi launch."""
+        e_c = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]
+        e_u = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]
+        nz = [torch.randn_like(perm_like) for _ in range(n)]
+        xs = torch.empty((n,) + tuple(x_in.shape), device=dev)
+        if n == 1:
+            eng.step(params[k0], x_in, e_c[0], e_u[0], nz[0], scale, xs[0], None)
+        else:
+            eng.step_multi(params[k0:k0 + n], x_in, e_c, e_u, nz, scale, xs, None)
+        return xs[n - 1]
+
+    def chunks(k0, n):
+        return [(k0 + i, min(C, n - i)) for i in range(0, n, C)]
+
+    for k0, n in chunks(0, W):
+        x = run_chunk(k0, n, x)
     sync_all()
     clocks = ClockSampler(local_rank)
     clocks.start()
     launches0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    timed = chunks(W, K)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in timed]
     sync_all()
-    for k in range(K):
+    for j, (k0, n) in enumerate(timed):
         flush_buf.zero_()                      # evict L2 (126 MB) - outside the event bracket
-        ev[k][0].record()
-        x = one_step(W + k, x)
-        ev[k][1].record()
+        ev[j][0].record()
+        x = run_chunk(k0, n, x)
+        ev[j][1].record()
     sync_all()
     launches = eng.launch_count() - launches0
     clk = clocks.stop()
     t_ms = sum(s.elapsed_time(e) for s, e in ev)
     assert torch.isfinite(x).all(), "sampler diverged"
 
-    # dominant kernel alone (the ls_step launch without the torch RNG launches), for the roofline
+    # dominant kernel alone (the ls_step_multi launch without the torch RNG launches), for the roofline
     g = torch.Generator(device=dev).manual_seed(5)
-    e_c = torch.randn(B, 1, 512, device=dev, generator=g)
-    e_u = torch.randn(B, 1, 512, device=dev, generator=g)
-    nz = torch.randn(*shape, device=dev, generator=g)
-    x_out = torch.empty_like(x)
-    kk = min(K, 50)
+    nk = min(C, K)
+    e_c = [torch.randn(B, 1, 512, device=dev, generator=g) for _ in range(nk)]
+    e_u = [torch.randn(B, 1, 512, device=dev, generator=g) for _ in range(nk)]
+    nz = [torch.randn(*shape, device=dev, generator=g) for _ in range(nk)]
+    xs = torch.empty((nk,) + tuple(x.shape), device=dev)
+    kk = max(3, min(K, 50) // nk)
     evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(kk)]
     l0 = eng.launch_count()
     for k in range(kk):
         flush_buf.zero_()
         evk[k][0].record()
-        eng.step(params[W + k], x, e_c, e_u, nz, scale, x_out, None)
+        if nk == 1:
+            eng.step(params[W], x, e_c[0], e_u[0], nz[0], scale, xs[0], None)
+        else:
+            eng.step_multi(params[W:W + nk], x, e_c, e_u, nz, scale, xs, None)
         evk[k][1].record()
     torch.cuda.synchronize()
-    kern_ms = sum(s.elapsed_time(e) for s, e in evk) / kk
-    launches_per_step = (eng.launch_count() - l0) / kk
+    kern_ms = sum(s.elapsed_time(e) for s, e in evk) / kk          # per launch of nk steps
+    launches_per_step = (eng.launch_count() - l0) / (kk * nk)
 
     # ------------------------------------------------------------------ end to end (host buffers)
     n_e2e = min(K, T_FULL)
     h2d = sum(v.numel() * v.element_size() for k_, v in y_pinned.items()
               if torch.is_tensor(v) and k_ in ("audio_input", "origin_x", "vid_indices", "scale", "emo"))
     sample_fn = diffusion.ddim_sample_loop if ddim else diffusion.p_sample_loop
+    diffusion.fused_chunk = C
 
     def e2e_once():
         yk = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in y_pinned.items()}
@@ -303,7 +323,8 @@ def main():
         peak, peak_src = measured_peaks()
         steps_per_s = world * K / (t_ms / 1e3)
         flop_step = B * FLOP_PER_SAMPLE_STEP[a.dataset]
-        achieved = flop_step / (kern_ms / 1e3) / 1e12
+        flop_launch = nk * flop_step
+        achieved = flop_launch / (kern_ms / 1e3) / 1e12
         impl = eng.get_impl()
         line = {
             "metric": "denoising-steps/sec", "value": steps_per_s,
@@ -321,8 +342,8 @@ def main():
             "gpu_launches": launches,
             "launches_per_step": launches_per_step,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(impl, a.dataset, B), "peak_source": peak_src,
-                         "kernel_ms": kern_ms, "flop_per_launch": flop_step,
+                         "frac": achieved / peak, "traffic": ncu_traffic(impl, a.dataset, B, nk), "peak_source": peak_src,
+                         "kernel_ms": kern_ms, "steps_per_launch": nk, "flop_per_launch": flop_launch,
                          "note": "algorithmic flops (BASELINE.md section 3): x3 of the bf16x3 split and padding not counted"},
             "clocks": clk,
         }

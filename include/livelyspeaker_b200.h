@@ -79,6 +79,19 @@ typedef struct ls_step_params {
   float c[8];
 } ls_step_params;
 
+/* Per-step buffers of ls_step_multi: the draws and outputs of ONE step, same meaning as
+ * the ls_step arguments of the same names.                                              */
+typedef struct ls_step_io {
+  const float* eps_cond;     /* [B,512] randn of the cond pass' reparameterize           */
+  const float* eps_uncond;   /* [B,512] ... of the uncond pass                            */
+  const float* noise;        /* step noise, strided (may be NULL when add_noise == 0)     */
+  int64_t noise_sb, noise_sj, noise_sf;
+  float* x_prev;             /* [B,J*D,F] sample after this step                          */
+  float* pred_x0;            /* [B,J*D,F] or NULL                                         */
+} ls_step_io;
+
+#define LS_MAX_FUSED_STEPS 16
+
 /* Which implementation ls_step / ls_cfg_forward use for the denoiser. */
 enum {
   LS_IMPL_AUTO = 0,       /* fused tcgen05 kernel when built in, else simt            */
@@ -149,6 +162,16 @@ int ls_step(ls_handle* h, int32_t B, const ls_step_params* p, const float* x_t,
             const float* eps_cond, const float* eps_uncond, const float* noise,
             int64_t noise_sb, int64_t noise_sj, int64_t noise_sf, const float* scale,
             float* x_prev, float* pred_x0, void* stream);
+
+/* n_steps (<= LS_MAX_FUSED_STEPS) consecutive iterations of the p_sample_loop /
+ * ddim_sample_loop body (gaussian_diffusion.py:718-743, 986-1014) in one launch.
+ * p and io are HOST arrays of n_steps entries in execution order; step k reads
+ * x_t (k = 0) or io[k-1].x_prev, so the x_prev buffers must be distinct and must
+ * not alias x_t when n_steps > 1.  Results equal n_steps calls of ls_step bit for
+ * bit; the fused kernel schedules (clip, step) items across the SMs, which removes
+ * the tail of a 512-clip batch on 148 SMs.  All mode fields must be 0 or 1.       */
+int ls_step_multi(ls_handle* h, int32_t B, int32_t n_steps, const ls_step_params* p,
+                  const ls_step_io* io, const float* x_t, const float* scale, void* stream);
 
 /* q_sample (gaussian_diffusion.py:240-258): out = c_x0*x0 + c_noise*noise, n elements. */
 int ls_q_sample(ls_handle* h, int64_t n, const float* x0, const float* noise,

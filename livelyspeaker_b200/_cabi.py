@@ -11,14 +11,15 @@ from ctypes import POINTER, byref, c_char_p, c_float, c_int32, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libls_b200.so")
+# LS_B200_LIB selects a diagnostic build of the same library (tools/build_variants.sh); never a fallback.
+LIB_PATH = os.environ.get("LS_B200_LIB") or os.path.join(_HERE, "csrc", "libls_b200.so")
 
 LS_IMPL_AUTO, LS_IMPL_SIMT, LS_IMPL_TC_BF16X3, LS_IMPL_TC_BF16 = 0, 1, 2, 3
 IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
-           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_q_sample", "ls_launch_count",
+           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_q_sample", "ls_launch_count",
            "ls_debug_buffer"]
 
 
@@ -31,6 +32,15 @@ class LsConfig(ctypes.Structure):
 class LsStepParams(ctypes.Structure):
     _fields_ = [("mode", c_int32), ("t_model", c_int32), ("clip_denoised", c_int32), ("add_noise", c_int32),
                 ("c", c_float * 8)]
+
+
+class LsStepIO(ctypes.Structure):
+    _fields_ = [("eps_cond", c_void_p), ("eps_uncond", c_void_p), ("noise", c_void_p),
+                ("noise_sb", c_int64), ("noise_sj", c_int64), ("noise_sf", c_int64),
+                ("x_prev", c_void_p), ("pred_x0", c_void_p)]
+
+
+MAX_FUSED_STEPS = 16     # LS_MAX_FUSED_STEPS
 
 
 class LsError(RuntimeError):
@@ -68,6 +78,8 @@ def load_library():
                                    c_void_p]
     lib.ls_step.argtypes = [c_void_p, c_int32, POINTER(LsStepParams), c_void_p, c_void_p, c_void_p, c_void_p,
                             c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ls_step_multi.argtypes = [c_void_p, c_int32, c_int32, POINTER(LsStepParams), POINTER(LsStepIO), c_void_p,
+                                  c_void_p, c_void_p]
     lib.ls_q_sample.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]
     lib.ls_launch_count.argtypes = [c_void_p]
     lib.ls_launch_count.restype = c_int64
@@ -266,6 +278,36 @@ class Engine:
                                          c_void_p(scale.data_ptr()),
                                          c_void_p(x_prev.data_ptr()) if x_prev is not None else None,
                                          c_void_p(pred_x0.data_ptr()) if pred_x0 is not None else None, _stream()))
+
+    def _noise_arg(self, noise):
+        """(tensor kept alive, ptr, sb, sj, sf) of a step-noise tensor whose (J,D) dims collapse."""
+        if noise is None:
+            return None, None, 0, 0, 0
+        sb, sj, sd, sf = noise.stride()
+        if noise.dtype != torch.float32 or noise.device != self.device or sj != sd * noise.shape[2]:
+            noise = _f32(noise, self.device)
+            sb, sj, sd, sf = noise.stride()
+        return noise, noise.data_ptr(), sb, sd, sf
+
+    def step_multi(self, params, x_t, eps_c, eps_u, noise, scale, x_prev, pred_x0):
+        """len(params) <= MAX_FUSED_STEPS consecutive steps in one launch (ls_step_multi).
+        eps_c / eps_u / noise: per-step lists; x_prev / pred_x0: dense [K,B,J,D,F] outputs
+        (pred_x0 may be None).  Step k starts from x_t (k = 0) or x_prev[k-1]."""
+        K = len(params)
+        B = x_t.shape[0]
+        P = (LsStepParams * K)(*params)
+        IO = (LsStepIO * K)()
+        keep = []
+        for k in range(K):
+            nz, nptr, sb, sj, sf = self._noise_arg(noise[k])
+            keep.append(nz)
+            IO[k].eps_cond, IO[k].eps_uncond = eps_c[k].data_ptr(), eps_u[k].data_ptr()
+            IO[k].noise, IO[k].noise_sb, IO[k].noise_sj, IO[k].noise_sf = nptr, sb, sj, sf
+            IO[k].x_prev = x_prev[k].data_ptr()
+            IO[k].pred_x0 = pred_x0[k].data_ptr() if pred_x0 is not None else None
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_step_multi(self.h, B, K, P, IO, c_void_p(x_t.data_ptr()),
+                                               c_void_p(scale.data_ptr()), _stream()))
 
     def q_sample(self, x0, noise, c_x0, c_noise):
         x0 = _f32(x0, self.device)

@@ -319,25 +319,63 @@ extern "C" int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int
   return lsk_cfg_combine(h, B, h->out_c, h->out_u, scale, out, s);
 }
 
+static int check_step(ls_handle* h, const ls_step_params* p, const ls_step_io* io, bool allow_mode2) {
+  if (p->mode < 0 || p->mode > (allow_mode2 ? 2 : 1)) return ls_fail(h, LS_EINVAL, "mode %d", p->mode);
+  if (!io->eps_cond || !io->eps_uncond) return ls_fail(h, LS_EINVAL, "null argument");
+  if (p->mode != 2 && !io->x_prev) return ls_fail(h, LS_EINVAL, "x_prev is NULL");
+  if (p->mode == 2 && !io->pred_x0) return ls_fail(h, LS_EINVAL, "mode 2 needs pred_x0");
+  if (p->mode != 2 && p->add_noise && !io->noise) return ls_fail(h, LS_EINVAL, "noise is NULL");
+  if (p->t_model < 0 || p->t_model >= h->cfg.max_timestep)
+    return ls_fail(h, LS_EINVAL, "t_model %d outside the embedding table [0,%d)", p->t_model, h->cfg.max_timestep);
+  return LS_OK;
+}
+
+static int step_simt(ls_handle* h, int B, const ls_step_params* p, const ls_step_io* io, const float* x_t,
+                     const float* scale, cudaStream_t s) {
+  int rc;
+  if ((rc = lsk_denoise_simt(h, B, x_t, nullptr, p->t_model, 3, io->eps_cond, io->eps_uncond, h->out_c, h->out_u, s)))
+    return rc;
+  return lsk_cfg_update(h, B, p, h->out_c, h->out_u, scale, x_t, io->noise, io->noise_sb, io->noise_sj, io->noise_sf,
+                        io->x_prev, io->pred_x0, s);
+}
+
 extern "C" int ls_step(ls_handle* h, int32_t B, const ls_step_params* p, const float* x_t, const float* eps_cond,
                        const float* eps_uncond, const float* noise, int64_t noise_sb, int64_t noise_sj,
                        int64_t noise_sf, const float* scale, float* x_prev, float* pred_x0, void* stream) {
   int rc = check_ready(h, B, true);
   if (rc) return rc;
-  if (!p || !x_t || !eps_cond || !eps_uncond || !scale) return ls_fail(h, LS_EINVAL, "null argument");
-  if (p->mode < 0 || p->mode > 2) return ls_fail(h, LS_EINVAL, "mode %d", p->mode);
-  if (p->mode != 2 && !x_prev) return ls_fail(h, LS_EINVAL, "x_prev is NULL");
-  if (p->mode == 2 && !pred_x0) return ls_fail(h, LS_EINVAL, "mode 2 needs pred_x0");
-  if (p->mode != 2 && p->add_noise && !noise) return ls_fail(h, LS_EINVAL, "noise is NULL");
-  if (p->t_model < 0 || p->t_model >= h->cfg.max_timestep)
-    return ls_fail(h, LS_EINVAL, "t_model %d outside the embedding table [0,%d)", p->t_model, h->cfg.max_timestep);
+  if (!p || !x_t || !scale) return ls_fail(h, LS_EINVAL, "null argument");
+  const ls_step_io io{eps_cond, eps_uncond, noise, noise_sb, noise_sj, noise_sf, x_prev, pred_x0};
+  if ((rc = check_step(h, p, &io, true))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
   const int impl = ls_get_impl(h);
   if (impl == LS_IMPL_TC_BF16X3 || impl == LS_IMPL_TC_BF16)
-    return lsf_step(h, B, p, impl == LS_IMPL_TC_BF16X3, x_t, eps_cond, eps_uncond, noise, noise_sb, noise_sj, noise_sf,
-                    scale, x_prev, pred_x0, s);
-  if ((rc = lsk_denoise_simt(h, B, x_t, nullptr, p->t_model, 3, eps_cond, eps_uncond, h->out_c, h->out_u, s))) return rc;
-  return lsk_cfg_update(h, B, p, h->out_c, h->out_u, scale, x_t, noise, noise_sb, noise_sj, noise_sf, x_prev, pred_x0, s);
+    return lsf_steps(h, B, 1, p, &io, impl == LS_IMPL_TC_BF16X3, x_t, scale, s);
+  return step_simt(h, B, p, &io, x_t, scale, s);
+}
+
+extern "C" int ls_step_multi(ls_handle* h, int32_t B, int32_t n_steps, const ls_step_params* p, const ls_step_io* io,
+                             const float* x_t, const float* scale, void* stream) {
+  int rc = check_ready(h, B, true);
+  if (rc) return rc;
+  if (!p || !io || !x_t || !scale) return ls_fail(h, LS_EINVAL, "null argument");
+  if (n_steps < 1 || n_steps > LS_MAX_FUSED_STEPS)
+    return ls_fail(h, LS_EINVAL, "n_steps %d outside [1,%d]", n_steps, LS_MAX_FUSED_STEPS);
+  for (int k = 0; k < n_steps; ++k) {
+    if ((rc = check_step(h, p + k, io + k, false))) return rc;
+    if (n_steps > 1) {
+      if (io[k].x_prev == x_t) return ls_fail(h, LS_EINVAL, "x_prev of step %d aliases x_t", k);
+      for (int j = 0; j < k; ++j)
+        if (io[j].x_prev == io[k].x_prev) return ls_fail(h, LS_EINVAL, "steps %d and %d share x_prev", j, k);
+    }
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int impl = ls_get_impl(h);
+  if (impl == LS_IMPL_TC_BF16X3 || impl == LS_IMPL_TC_BF16)
+    return lsf_steps(h, B, n_steps, p, io, impl == LS_IMPL_TC_BF16X3, x_t, scale, s);
+  for (int k = 0; k < n_steps; ++k)
+    if ((rc = step_simt(h, B, p + k, io + k, k == 0 ? x_t : io[k - 1].x_prev, scale, s))) return rc;
+  return LS_OK;
 }
 
 extern "C" int ls_q_sample(ls_handle* h, int64_t n, const float* x0, const float* noise, float c_x0, float c_noise,

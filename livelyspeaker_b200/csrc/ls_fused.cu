@@ -1,23 +1,39 @@
-// The fused denoising step: ONE persistent sm_100a kernel per step.
+// The fused denoising step(s): ONE persistent sm_100a kernel per launch of up to 16 steps.
 //
 //   _WrappedModel + ClassifierFreeSampleModel + RAG.forward (minus the hoisted terms) +
 //   p_mean_variance + p_sample / ddim_sample of the reference
 //   (respace.py:118-130, cfg_sampler.py:24-31, RAG.py:98-133, mlp_module.py:37-91,
 //    gaussian_diffusion.py:284-399, 507-558, 745-798) - see DESIGN.md "fused step kernel".
 //
-// Work unit (tile) = one clip, both guidance passes: 2*S token rows (S = 35 TED / 36 BEAT).
+// Work item (tile) = one clip at one step, both guidance passes: 2*S token rows (S = 35 TED / 36 BEAT).
+// A launch covers n_steps consecutive steps: item q = step * B + clip, CTA i takes q = i, i+grid, ...
+// Item (k, b) needs x of (k-1, b), produced >= 3 rounds earlier by another CTA and published through a
+// per-clip release/acquire counter, so the 512 clips of a batch no longer quantise to 4 rounds of 148.
+//
 // All GEMMs run TRANSPOSED on the tensor cores, D^T[channel, row] = W[channel, k] * U^T[k, row]:
-//   M = 128 output channels (4 M-tiles for d = 512), N = 80 rows (2*S padded), K = channels.
+//   M = 128 output channels (4 M-tiles for d = 512), N = rows of the tile, K = channels,
 // so the TMEM lane of an accumulator element is its CHANNEL and the column is its ROW:
 //   * each of the 512 epilogue threads owns one channel and keeps the fp32 residual stream
 //     h[row] of that channel in REGISTERS for the whole 8-layer stack;
-//   * TMEM holds only accumulators (4 M-tiles x 80 columns);
-//   * shared memory holds the bf16 hi/lo operand tile U (LayerNorm output) - the very same
-//     bytes serve as the K-major B operand of the channel-mix GEMM and as the MN-major A
-//     operand of the token-mix GEMM (ls_tc.cuh, validated by umma_probe.cu) - plus a
-//     2-slot ring of weight stages streamed from L2 by 1-D bulk async copies.
-// Precision: PRECISE = bf16x3 (hi*hi + lo*hi + hi*lo, fp32 accumulate) meets the
-// rtol 1e-3 / atol 1e-4 parity bar; !PRECISE = plain bf16 operands (fast mode).
+//   * TMEM holds only accumulators;
+//   * shared memory holds the bf16 operand tile U (LayerNorm output) - the very same bytes serve as
+//     the K-major B operand of the channel-mix GEMM and as the MN-major A operand of the token-mix
+//     GEMM (ls_tc.cuh, validated by umma_probe.cu) - plus a 4-slot ring of weight stages streamed
+//     from L2 by 1-D bulk async copies.
+// Precision: PRECISE = bf16x3 (hi*hi + hi*lo + lo*hi, fp32 accumulate) meets the rtol 1e-3 /
+// atol 1e-4 parity bar; !PRECISE = plain bf16 operands (fast mode).
+//
+// What bounds a GEMM phase is SHARED-MEMORY BANDWIDTH, not the tensor pipe: an SS-mode M=128,K=16 MMA
+// costs max(N/2, 32 + N/4) cycles (umma_bench2.cu: the 4 KB A block and the N*32 B of B are read at
+// 128 B/clk), and the weight ring fill shares that bandwidth.  Hence the operand tile stores, per
+// 64-channel block, the lo image (72 rows) directly followed by the hi image (72 rows): ONE N=144 MMA
+// reads a W_hi block once for both U_lo and U_hi (columns [0,72) and [72,144) of the accumulator),
+// a second N=80 MMA adds W_lo * U_hi into columns [72,152); the epilogue sums the two column ranges.
+//
+// LayerNorm 2 is off the critical path: the channel-mix operand is normalised with the statistics of
+// LayerNorm 1 of the same rows (already known), alpha2 is folded into the weight tape and the exact
+// statistics - reduced while the GEMM runs - enter as a per-row scale / shift in the GEMM epilogue:
+//   W.(alpha*((h-mu)*rho)+beta)+b = (rho/s)*acc + ((m-mu)*rho)*S_c + t_c,  acc = (W.alpha)*((h-m)*s).
 //
 // Warp roles (20 warps): 0-15 epilogue (thread id == channel), 16 weight producer,
 // 17 MMA issuer + TMEM owner, 18-19 idle; warps 16-19 give most of their registers to the
@@ -37,42 +53,68 @@ constexpr int NT_EPI = 512;
 constexpr int NT_ALL = 640;                     // 16 epilogue warps + 1 producer + 1 MMA + 2 idle (register donors)
 constexpr int REGS_EPI = 112;                   // setmaxnreg budgets must conserve the launch allocation:
 constexpr int REGS_AUX = 32;                    // 512*112 + 128*32 == 640*96 (a larger total blocks forever in setmaxnreg.inc)
-constexpr int NROW = 80;                       // MMA N (rows of a tile, padded)
-constexpr int RGS = 9;                         // 8-row groups stored per 64-channel block (72 rows)
-constexpr uint32_t CBS = RGS * 1024;           // bytes between 64-channel blocks of U
-constexpr uint32_t U_BYTES = 8 * CBS;          // one of U_hi / U_lo
-constexpr uint32_t SLOT = 16384;               // ring slot = tape stage pitch
+constexpr int NROW = 80;                        // MMA N of a single-image product (rows of a tile, padded)
+constexpr int NCAT = 144;                       // MMA N of the concatenated [U_lo ; U_hi] operand
+constexpr int RGS = 9;                          // 8-row groups per image (72 rows)
+constexpr uint32_t HALF_BLK = RGS * 1024;       // one image (lo or hi) of a 64-channel block
+constexpr uint32_t CBS = 2 * HALF_BLK;          // bytes between 64-channel blocks of U: [lo image][hi image]
+constexpr uint32_t HI_OFF = HALF_BLK;           // hi image inside a block
+constexpr uint32_t U_BYTES = 8 * CBS;
+constexpr uint32_t SLOT = 16384;                // ring slot = tape stage pitch
 constexpr int NSLOT = 4;
 #ifndef LS_MULTICAST
 #define LS_MULTICAST 1   // 1: weight stages fetched half by each CTA of the pair and multicast to both
 #endif
-constexpr uint32_t W_HALF = 16384;             // 128 x 64 bf16 weight block (hi or lo) = one stage
-constexpr uint32_t WBLK_BLK = 10 * 1024;       // token-mix weights: 80 rows x 64 k = one stage
+#ifndef LS_NOFETCH
+#define LS_NOFETCH 0     // diagnostic: 1 = the producer signals stages without copying (garbage results, pure MMA timing)
+#endif
+#ifndef LS_MMA_PROF
+#define LS_MMA_PROF 0    // diagnostic: 1 = the MMA warp accounts its cycles (ring waits / operand waits / total) of CTA 0
+#endif
+constexpr uint32_t W_HALF = 16384;              // 128 x 64 bf16 weight block (hi or lo) = one stage
+constexpr uint32_t WBLK_BLK = 10 * 1024;        // token-mix weights: 80 rows x 64 k = one stage
+// TMEM columns.  Channel-type GEMMs (input projection, channel mix, head) use 3 rotating buffers of
+// ACC_COLS: [0,72) W_hi*U_lo, [72,144) W_hi*U_hi + W_lo*U_hi, [144,152) overhang of the N=80 product.
+// Token-mix accumulators (N=80, one per M-tile) alias them; the two kinds are never live together.
+constexpr int ACC_COLS = 152;
+constexpr int NACC = 3;
+constexpr int CAT_HI = 72;                      // first column of the hi-image product in a buffer
+constexpr int KMAX = LS_MAX_FUSED_STEPS;
 
 // shared memory map (offsets from a 1024-aligned base)
-constexpr uint32_t OFF_UHI = 0;
-constexpr uint32_t OFF_ULO = U_BYTES;
-constexpr uint32_t OFF_PAD = 2 * U_BYTES;               // 1024 zero bytes: row group 9 of the last block
+constexpr uint32_t OFF_U = 0;
+constexpr uint32_t OFF_PAD = U_BYTES;                   // 1024 zero bytes: row group 9 of the last hi image
 constexpr uint32_t OFF_RING = OFF_PAD + 1024;
 constexpr uint32_t OFF_PART = OFF_RING + NSLOT * SLOT;  // [16 warps][72 rows] float2 LN partial sums
 constexpr uint32_t OFF_STATS = OFF_PART + 16 * 72 * 8;  // [72] float2 (mean, rstd)
-constexpr uint32_t OFF_BTOK = OFF_STATS + 72 * 8;       // [72] float token-mix bias
+constexpr uint32_t OFF_GD = OFF_STATS + 72 * 8;         // [72] float2 channel-mix epilogue (row scale, row shift)
+constexpr uint32_t OFF_BTOK = OFF_GD + 72 * 8;          // [72] float token-mix bias
 constexpr uint32_t OFF_BARS = OFF_BTOK + 72 * 4;        // mbarriers
-constexpr uint32_t OFF_TMEM = OFF_BARS + 16 * 8;
+constexpr uint32_t OFF_TMEM = OFF_BARS + 24 * 8;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_DYN = SMEM_USED + 1024;         // + alignment slack
+static_assert(SMEM_DYN <= 232448, "shared memory budget");
+static_assert(NACC * ACC_COLS <= 512 && 4 * NROW <= 512, "TMEM budget");
 
-enum { BAR_FULL0 = 0, BAR_EMPTY0 = 4, BAR_UREADY0 = 8, BAR_ACC0 = 12 };   // indices into the mbarrier array
+enum { BAR_FULL0 = 0, BAR_EMPTY0 = 4, BAR_UREADY0 = 8, BAR_ACC0 = 12, BAR_DRAIN = 16 };   // indices into the mbarrier array
+
+struct StepIO {
+  const float* eps_c; const float* eps_u; const float* noise;
+  long long nsb, nsj, nsf;
+  float* x_prev; float* pred_x0;
+};
 
 struct FusedParams {
   const uint8_t* tape;     // weight stages, SLOT bytes apart
-  int n_layers, JD, KIN, MH, B;
+  int n_layers, JD, KIN, MH, B, n_steps;
   LsWeights w;
+  const float* Sc;         // [n_layers][512] sum_k W_ch[c,k]*alpha2[k]
+  const float* tc;         // [n_layers][512] sum_k W_ch[c,k]*beta2[k] + b_ch[c]
   const float* A; const float* P; const float* z_mu; const float* z_lv; const float* emo_tok;
-  const float* x_t; const float* eps_c; const float* eps_u; const float* noise; const float* scale;
-  long long nsb, nsj, nsf;
-  float* x_prev; float* pred_x0;
-  ls_step_params sp;
+  const float* x_in; const float* scale;
+  int* flags;              // [B] steps completed per clip in this launch (n_steps > 1)
+  ls_step_params sp[KMAX];
+  StepIO io[KMAX];
   long long* timing;       // debug (LS_FUSED_TIMING=1): clock64 stamps of block 0, threads 0 and 511
 };
 
@@ -81,18 +123,26 @@ __device__ __forceinline__ float silu_fast(float z) { return __fdividef(z, 1.f +
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// hi/lo bf16 split of v, stored at byte offset `off` of U_hi (and U_lo)
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
 }
-// u_s = shared-space address of U_hi
+// hi/lo bf16 split of v, stored at byte offset `off` of the lo image (hi image = + HI_OFF); u_s = shared-space address of U
 template <bool PRECISE>
 __device__ __forceinline__ void store_split(uint32_t u_s, uint32_t off, float v) {
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  sts_u16(u_s + off, __bfloat16_as_ushort(hi));
+  sts_u16(u_s + HI_OFF + off, __bfloat16_as_ushort(hi));
   if (PRECISE) {
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    sts_u16(u_s + OFF_ULO + off, __bfloat16_as_ushort(lo));
+    sts_u16(u_s + off, __bfloat16_as_ushort(lo));
   }
 }
 
@@ -103,14 +153,14 @@ template <bool PRECISE>
 __device__ __forceinline__ void store_split2(uint32_t u_s, uint32_t off0, uint32_t off1, float v0, float v1) {
   const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);      // .x = v0 (low half), .y = v1 (high half)
   const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi);
-  sts_u16(u_s + off0, (uint16_t)(hb & 0xFFFFu));
-  sts_u16(u_s + off1, (uint16_t)(hb >> 16));
+  sts_u16(u_s + HI_OFF + off0, (uint16_t)(hb & 0xFFFFu));
+  sts_u16(u_s + HI_OFF + off1, (uint16_t)(hb >> 16));
   if (PRECISE) {
     const float r0 = v0 - __uint_as_float(hb << 16), r1 = v1 - __uint_as_float(hb & 0xFFFF0000u);
     const __nv_bfloat162 lo = __floats2bfloat162_rn(r0, r1);
     const uint32_t lb = *reinterpret_cast<const uint32_t*>(&lo);
-    sts_u16(u_s + OFF_ULO + off0, (uint16_t)(lb & 0xFFFFu));
-    sts_u16(u_s + OFF_ULO + off1, (uint16_t)(lb >> 16));
+    sts_u16(u_s + off0, (uint16_t)(lb & 0xFFFFu));
+    sts_u16(u_s + off1, (uint16_t)(lb >> 16));
   }
 }
 
@@ -118,10 +168,12 @@ __device__ __forceinline__ uint32_t row_off(uint32_t pre_off, int n) {
   return (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
 }
 
-// Per-row (sum, sum of squares) over the 512 channels -> stats[row] = (mean, 1/std).
-// h[] holds this thread's channel; `shift` rows come from the previous stats (robust
-// single-pass variance), or 0 when use_shift is false.
-template <int R>
+// Per-row (sum, sum of squares) over the 512 channels.  h[] holds this thread's channel; `shift` rows
+// come from the previous stats (robust single-pass variance), or 0 when use_shift is false.
+//   CORR == 0: stats[row] = (mean, 1/std).
+//   CORR == 1: (m, s) = stats[row] is what the operand tile was normalised with; the exact (mu, rho)
+//              give the channel-mix epilogue's gd[row] = (rho / s, (m - mu) * rho) and replace stats[row].
+template <int R, int CORR>
 __device__ __forceinline__ void ln_stats(const float (&h)[72], uint8_t* sm, bool use_shift) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float2* part = reinterpret_cast<float2*>(sm + OFF_PART);
@@ -171,17 +223,25 @@ __device__ __forceinline__ void ln_stats(const float (&h)[72], uint8_t* sm, bool
       ss += p.x;
       qq += p.y;
     }
-    const float sh = use_shift ? stats[tid].x : 0.f;
+    const float2 old = stats[tid];
+    const float sh = use_shift ? old.x : 0.f;
     const float md = ss * (1.f / 512.f);
     const float var = fmaxf(qq * (1.f / 512.f) - md * md, 0.f);
-    stats[tid] = make_float2(sh + md, rsqrtf(var + 1e-5f));
+    const float mu = sh + md, rho = rsqrtf(var + 1e-5f);
+    if (CORR) {
+      float2* gd = reinterpret_cast<float2*>(sm + OFF_GD);
+      gd[tid] = make_float2(__fdividef(rho, old.y), (old.x - mu) * rho);
+    }
+    stats[tid] = make_float2(mu, rho);
   }
   epi_bar();
 }
 
-// LayerNorm of h -> bf16 (hi, lo) operand tile.  pre = smem address of (row 0, channel c)
+// LayerNorm of h -> bf16 (hi, lo) operand tile.  pre = offset of (row 0, channel c) in the lo image
 // with the chunk bits at [4,7): row n lives at (pre ^ ((n&7)<<4)) + (n&7)*128 + (n>>3)*1024.
-template <int R, bool PRECISE>
+// AFFINE: (h - mean) * rstd * alpha + beta (LayerNorm 1).  !AFFINE: (h - mean) * rstd only (the
+// provisional normalisation of the channel-mix operand; alpha/beta live in the tape / epilogue).
+template <int R, bool PRECISE, bool AFFINE>
 __device__ __forceinline__ void ln_store(const float (&h)[72], uint8_t* sm, uint32_t u_s, uint32_t pre_off, float alpha,
                                          float beta) {
   const float2* stats = reinterpret_cast<const float2*>(sm + OFF_STATS);
@@ -189,21 +249,23 @@ __device__ __forceinline__ void ln_store(const float (&h)[72], uint8_t* sm, uint
 #pragma unroll
   for (int n = 0; n < R; n += 2) {
     const float2 s0 = stats[n], s1 = stats[n + 1];
-    const float u0 = fmaf((h[n] - s0.x) * s0.y, alpha, beta);
-    const float u1 = fmaf((h[n + 1] - s1.x) * s1.y, alpha, beta);
+    float u0 = (h[n] - s0.x) * s0.y, u1 = (h[n + 1] - s1.x) * s1.y;
+    if (AFFINE) {
+      u0 = fmaf(u0, alpha, beta);
+      u1 = fmaf(u1, alpha, beta);
+    }
     store_split2<PRECISE>(u_s, row_off(pre_off, n), row_off(pre_off, n + 1), u0, u1);
   }
 }
 
-// Walk the accumulator columns [0, R) of this thread's TMEM lane in chunks of 16 (+8) and hand
+// Walk the token-mix accumulator columns [0, R) of this thread's TMEM lane in chunks of 16 (+8) and hand
 // (row, value) to f with compile-time row indices.  Must be executed by whole warps.
 template <int R, class F>
-__device__ __forceinline__ void for_acc(uint32_t taddr, F&& f) {
+__device__ __forceinline__ void for_acc_tok(uint32_t taddr, F&& f) {
 #pragma unroll
   for (int c0 = 0; c0 < 64; c0 += 16) {
     float v[16];
     tmem_ld16(taddr + c0, v);
-    tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 16; ++j)
       if (c0 + j < R) f(c0 + j, v[j]);
@@ -211,10 +273,28 @@ __device__ __forceinline__ void for_acc(uint32_t taddr, F&& f) {
   {
     float v[8];
     tmem_ld8(taddr + 64, v);
-    tmem_ld_wait();
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (64 + j < R) f(64 + j, v[j]);
+  }
+}
+
+// Same for a channel-type accumulator buffer: value(row) = D[row] (W_hi*U_lo) + D[72 + row] (the rest).
+template <int R, bool PRECISE, class F>
+__device__ __forceinline__ void for_acc_cat(uint32_t taddr, F&& f) {
+#pragma unroll
+  for (int c0 = 0; c0 < 72; c0 += 8) {
+    float a[8], b[8];
+    if (PRECISE) {
+      tmem_ld8x2(taddr + c0, taddr + CAT_HI + c0, a, b);
+    } else {
+      tmem_ld8(taddr + CAT_HI + c0, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < R) f(c0 + j, a[j] + b[j]);
   }
 }
 
@@ -225,7 +305,7 @@ template <int S>
 struct TokBias { static constexpr bool kInGemm = (2 * S + 1 <= 72); };
 
 template <int S, bool PRECISE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_step_kernel(const FusedParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
   constexpr int R = 2 * S;            // real rows of a tile
   constexpr int NPRE = S - LS_F;      // prefix tokens per pass
   static_assert(R <= 72, "tile rows");
@@ -246,21 +326,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       mbar_init(&bars[BAR_UREADY0 + m], 128);     // the 4 warps that own the channels of M-tile m
       mbar_init(&bars[BAR_ACC0 + m], 1);
     }
+    mbar_init(&bars[BAR_DRAIN], 128);             // M-tile 0's warps have read accumulator buffer 0 (M-tile 3 reuses it)
     mbar_fence_init();
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
   __syncthreads();
   if (TokBias<S>::kInGemm && tid < LS_D)          // the ones row (hi = 1.0, lo = 0) - never overwritten
-    sts_u16(smem_u32(sm + OFF_UHI) + tile_off(R, tid, CBS), (uint16_t)0x3F80u);
+    sts_u16(smem_u32(sm + OFF_U) + HI_OFF + tile_off(R, tid, CBS), (uint16_t)0x3F80u);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   cluster_sync_all();             // barriers of both CTAs initialised before any multicast touches them
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   // The two CTAs of a cluster consume ONE weight stream (every stage is fetched half by each CTA and
-  // multicast to both), so they run the same number of rounds; a CTA without a real clip in the
-  // last round recomputes clip B-1 and writes nothing.
-  const int n_rounds = (p.B + (int)gridDim.x - 1) / (int)gridDim.x;
+  // multicast to both), so they run the same number of rounds; a CTA without a real item in the
+  // last round recomputes item 0 and writes nothing.
+  const int n_items = p.B * p.n_steps;
+  const int n_rounds = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
   const uint32_t cta_rank = cluster_ctarank();
 
   if (warp >= 16) {
@@ -298,6 +380,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           stage = 8u * (uint32_t)KIN + 68u * (uint32_t)n_layers + 2u * (q - q_in - 34u * (uint32_t)n_layers);
         }
         mbar_wait_s(empty_s, ((it / NSLOT) & 1) ^ 1);                   // (both CTAs are) done with the slot
+#if LS_NOFETCH
+        mbar_arrive_expect_tx_s(full_s, 0);
+        continue;
+#endif
         mbar_arrive_expect_tx_s(full_s, bytes);
 #if LS_MULTICAST
         const uint32_t half = bytes >> 1;
@@ -310,24 +396,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
    } else if (warp == 17) {
     // ================= MMA issuer ==========================================================
     {   // all 32 lanes run this role in lock step; one elected lane issues (see ls_tc.cuh)
-      uint32_t it = 0, uphase = 0;
+      uint32_t it = 0, uphase = 0, dphase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);    // provably warp-uniform copy
-      constexpr uint32_t id_kk = idesc_bf16(128, NROW, 0, 0), id_mk = idesc_bf16(128, NROW, 1, 0);
+      constexpr uint32_t id_cat = idesc_bf16(128, NCAT, 0, 0), id_kk = idesc_bf16(128, NROW, 0, 0),
+                         id_mk = idesc_bf16(128, NROW, 1, 0);
       // Descriptor words: high word constant per layout, low word = (addr >> 4) | LBO field.
       constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
-      const uint32_t u_s = smem_u32(sm + OFF_UHI);
-      const uint32_t uk = desc_lo32(u_s, 16);          // K-major view of U_hi   (U_lo = + U_BYTES/16)
-      const uint32_t um = desc_lo32(u_s, CBS);         // MN-major view of U_hi
-      constexpr uint32_t LO = U_BYTES >> 4;            // descriptor-address distance U_hi -> U_lo
+      const uint32_t u_s = smem_u32(sm + OFF_U);
+      const uint32_t uk = desc_lo32(u_s, 16);          // K-major view of block 0 from its lo image
+      const uint32_t um = desc_lo32(u_s, CBS);         // MN-major view of the lo image
+      constexpr uint32_t HI = HI_OFF >> 4;             // descriptor-address distance lo image -> hi image
+      constexpr uint32_t BLK = CBS >> 4;               // ... between 64-channel blocks
+#if LS_MMA_PROF
+      long long prof_ring = 0, prof_u = 0;
+      const long long prof_t0 = clock64();
+#define LS_PROF(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
+#else
+#define LS_PROF(acc, stmt) { stmt; }
+#endif
       auto wait_u_all = [&]() {       // whole operand tile published (K = all channels)
+        LS_PROF(prof_u, {
 #pragma unroll
         for (int m = 0; m < 4; ++m) mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + m), uphase & 1);
+        })
         ++uphase;
         tc_fence_after_sync();
       };
       auto wait_stage = [&]() -> uint32_t {       // -> descriptor low word of the next ring slot
         const uint32_t slot = it % NSLOT, ph = (it / NSLOT) & 1;
-        mbar_wait_s(bars_s + 8 * (BAR_FULL0 + slot), ph);
+        LS_PROF(prof_ring, mbar_wait_s(bars_s + 8 * (BAR_FULL0 + slot), ph);)
         tc_fence_after_sync();
         return desc_lo32(ring_s + slot * SLOT, 16);
       };
@@ -339,19 +436,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
 #endif
         ++it;
       };
-      // D[mt] (+)= W[128 x 64 block] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
+      // D[buffer] (+)= W[128 x 64 block] * U[:, 64*kc .. +64]^T   (weights = A, K-major; U = B, K-major)
+      //   PRECISE: W_hi x [U_lo ; U_hi] -> columns [0,144), then W_lo x U_hi -> columns [72,152)
+      //   else   : W_hi x U_hi -> columns [72,152)
       auto gemm_pair = [&](uint32_t d, uint32_t ub, bool first) {
         uint32_t wl = wait_stage();
-#pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) {
-          umma_bf16_split_elect(d, wl + 2 * ks, DH, ub + 2 * ks, DH, id_kk, (first && ks == 0) ? 0u : 1u);
-          if (PRECISE) umma_bf16_split_elect(d, wl + 2 * ks, DH, ub + LO + 2 * ks, DH, id_kk, 1u);
-        }
-        release_stage();
         if (PRECISE) {
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_bf16_split_elect(d, wl + 2 * ks, DH, ub + 2 * ks, DH, id_cat, (first && ks == 0) ? 0u : 1u);
+          release_stage();
           wl = wait_stage();
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) umma_bf16_split_elect(d, wl + 2 * ks, DH, ub + 2 * ks, DH, id_kk, 1u);
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_bf16_split_elect(d + CAT_HI, wl + 2 * ks, DH, ub + HI + 2 * ks, DH, id_kk, 1u);
+          release_stage();
+        } else {
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_bf16_split_elect(d + CAT_HI, wl + 2 * ks, DH, ub + HI + 2 * ks, DH, id_kk, (first && ks == 0) ? 0u : 1u);
           release_stage();
         }
       };
@@ -360,9 +463,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         wait_u_all();
 #pragma unroll 1
         for (int mt = 0; mt < 4; ++mt) {
-          if (mt < n_mt)
+          if (mt < n_mt) {
+            if (mt == NACC) {         // buffer 0 again: M-tile 0's epilogue must have read it
+              mbar_wait_s(bars_s + 8 * BAR_DRAIN, dphase & 1);
+              ++dphase;
+              tc_fence_after_sync();
+            }
 #pragma unroll 1
-            for (int kc = 0; kc < n_kc; ++kc) gemm_pair(tmem_u + (uint32_t)mt * NROW, uk + (uint32_t)kc * (CBS >> 4), kc == 0);
+            for (int kc = 0; kc < n_kc; ++kc)
+              gemm_pair(tmem_u + (uint32_t)(mt % NACC) * ACC_COLS, uk + (uint32_t)kc * BLK, kc == 0);
+          }
           umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));    // M-tiles without work still flip their barrier
         }
       };
@@ -384,17 +494,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           it -= NW;
 #pragma unroll 1
           for (uint32_t mt = 0; mt < 4; ++mt) {
-            mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + mt), uphase & 1);
+            LS_PROF(prof_u, mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + mt), uphase & 1);)
             tc_fence_after_sync();
             const uint32_t d = tmem_u + mt * NROW;
-            const uint32_t ua = um + 2 * mt * (CBS >> 4);
+            const uint32_t ua = um + 2 * mt * BLK;         // lo image of this M-tile's channels, MN-major
 #pragma unroll
             for (uint32_t ks = 0; ks < 5; ++ks) {
               const uint32_t bw = wl[ks >> 2] + 2 * (ks & 3), ao = ua + ks * (2048 >> 4);
-              umma_bf16_split_elect(d, ao, DH, bw, DH, id_mk, ks == 0 ? 0u : 1u);
+              umma_bf16_split_elect(d, ao + HI, DH, bw, DH, id_mk, ks == 0 ? 0u : 1u);
               if (PRECISE) {
-                umma_bf16_split_elect(d, ao + LO, DH, bw, DH, id_mk, 1u);
-                umma_bf16_split_elect(d, ao, DH, wl[NW - 2 + (ks >> 2)] + 2 * (ks & 3), DH, id_mk, 1u);
+                umma_bf16_split_elect(d, ao, DH, bw, DH, id_mk, 1u);
+                umma_bf16_split_elect(d, ao + HI, DH, wl[NW - 2 + (ks >> 2)] + 2 * (ks & 3), DH, id_mk, 1u);
               }
             }
             umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));
@@ -406,6 +516,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         }
         gemm_all(MH, 8);                                   // output head
       }
+#if LS_MMA_PROF
+      if (p.timing != nullptr && blockIdx.x == 0 && lane == 0) {
+        p.timing[508] = prof_ring;
+        p.timing[509] = prof_u;
+        p.timing[510] = clock64() - prof_t0;
+        p.timing[511] = n_rounds;
+      }
+#endif
     }
    }
   } else {
@@ -413,11 +531,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
     // ================= epilogue: thread == channel ==========================================
     const int c = tid;
     const int mt = warp >> 2;
-    const uint32_t lane_taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * NROW;
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t taddr_tok = lane_base + (uint32_t)mt * NROW;
+    const uint32_t taddr_cat = lane_base + (uint32_t)(mt % NACC) * ACC_COLS;
     const uint32_t pre_off = (uint32_t)(c >> 6) * CBS + (uint32_t)(((c & 63) >> 3) << 4) + (uint32_t)(c & 7) * 2u;
     float* btok_s = reinterpret_cast<float*>(sm + OFF_BTOK);
-    const uint32_t u_s = smem_u32(sm + OFF_UHI);
-    const float emb = p.w.emb_table[(size_t)p.sp.t_model * LS_D + c];
+    const float2* gd = reinterpret_cast<const float2*>(sm + OFF_GD);
+    const uint32_t u_s = smem_u32(sm + OFF_U);
     uint32_t aphase = 0;
     auto wait_acc = [&]() {
       mbar_wait(&bars[BAR_ACC0 + mt], aphase & 1);
@@ -430,22 +550,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       tc_fence_before_sync();
       mbar_arrive(&bars[BAR_UREADY0 + mt]);
     };
+    auto drained = [&](int n_mt) {  // accumulator buffer 0 read: M-tile 3 of the same GEMM may overwrite it
+      if (n_mt > NACC && mt == 0) {
+        tc_fence_before_sync();
+        mbar_arrive(&bars[BAR_DRAIN]);
+      }
+    };
     float h[72];
     int tix = 0;
-    auto stamp = [&]() {
-      if (p.timing != nullptr && blockIdx.x == 0 && (tid == 0 || tid == 511) && tix < 256)
-        p.timing[(tid ? 256 : 0) + tix++] = clock64();
-    };
 
     for (int round = 0; round < n_rounds; ++round) {
-      const int b_raw = (int)blockIdx.x + round * (int)gridDim.x;
-      const bool valid = b_raw < p.B;
-      const int b = valid ? b_raw : p.B - 1;
+      auto stamp = [&]() {
+        if (p.timing != nullptr && round == 0 && blockIdx.x == 0 && (tid == 0 || tid == 511) && tix < 256)
+          p.timing[(tid ? 256 : 0) + tix++] = clock64();
+      };
+      const int q_raw = (int)blockIdx.x + round * (int)gridDim.x;
+      const bool valid = q_raw < n_items;
+      const int q = valid ? q_raw : 0;
+      const int k = q / p.B, b = q - k * p.B;           // step within this launch, clip
+      const ls_step_params& sp = p.sp[k];
+      const StepIO& io = p.io[k];
+      const float* x_t = (k == 0) ? p.x_in : p.io[k - 1].x_prev;
+      if (k > 0) {                  // x of (k-1, b) comes from another CTA
+        if (tid == 0)
+          while (ld_acquire_gpu(p.flags + b) < k) __nanosleep(64);
+        epi_bar();
+      }
+      const float emb = p.w.emb_table[(size_t)sp.t_model * LS_D + c];
       // ---- X operand: x_t[b] (hi, lo) into rows p*S + NPRE + f, k = j ----------------------
-      const float* xb = p.x_t + (size_t)b * p.JD * LS_F;
+      const float* xb = x_t + (size_t)b * p.JD * LS_F;
       for (int i = tid; i < p.JD * LS_F; i += NT_EPI) {
         const int j = i / LS_F, f = i - j * LS_F;
-        const float v = xb[i];
+        const float v = __ldcg(xb + i);
         store_split<PRECISE>(u_s, tile_off(NPRE + f, j, CBS), v);
         store_split<PRECISE>(u_s, tile_off(S + NPRE + f, j, CBS), v);
       }
@@ -454,8 +590,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       // ---- residual stream init: hoisted terms now, projection result when it lands --------
       {
         const float mu = p.z_mu[(size_t)b * LS_D + c], sd = __expf(0.5f * p.z_lv[(size_t)b * LS_D + c]);
-        h[0] = fmaf(p.eps_c[(size_t)b * LS_D + c], sd, mu);
-        h[S] = fmaf(p.eps_u[(size_t)b * LS_D + c], sd, mu);
+        h[0] = fmaf(io.eps_c[(size_t)b * LS_D + c], sd, mu);
+        h[S] = fmaf(io.eps_u[(size_t)b * LS_D + c], sd, mu);
         if (NPRE == 2) h[1] = h[S + 1] = p.emo_tok[(size_t)b * LS_D + c];
         const float* Pb = p.P + (size_t)b * LS_F * LS_D + c;
         const float* Ab = p.A + (size_t)b * LS_F * LS_D + c;
@@ -467,38 +603,45 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         }
       }
       wait_acc();
-      for_acc<R>(lane_taddr, [&](int n, float v) {
+      for_acc_cat<R, PRECISE>(taddr_cat, [&](int n, float v) {
         if ((n % S) >= NPRE) h[n] += v;          // prefix-token rows keep their direct values
       });
+      drained(4);
       stamp();   // 1: input projection consumed
 
       for (int l = 0; l < p.n_layers; ++l) {
         const LsLayerW L = p.w.layer[l];
-        const float a1 = L.ln1_a[c], b1 = L.ln1_b[c], a2 = L.ln2_a[c], b2 = L.ln2_b[c], bch = L.b_ch[c];
-        if (tid < S) btok_s[tid] = btok_s[S + tid] = L.b_tok[tid];
+        const float a1 = L.ln1_a[c], b1 = L.ln1_b[c];
+        const float Sc = p.Sc[l * LS_D + c], tc = p.tc[l * LS_D + c];
+        if (!TokBias<S>::kInGemm && tid < S) btok_s[tid] = btok_s[S + tid] = L.b_tok[tid];
         // x = x + emb ; LN1 ; -> operand tile
 #pragma unroll
         for (int n = 0; n < R; ++n) h[n] += emb;
-        if (l == 0) ln_stats<R>(h, sm, false);     // provisional means for the shift
-        ln_stats<R>(h, sm, true);
+        if (l == 0) ln_stats<R, 0>(h, sm, false);     // provisional means for the shift
+        ln_stats<R, 0>(h, sm, true);
         stamp();   // LN1 stats done
-        ln_store<R, PRECISE>(h, sm, u_s, pre_off, a1, b1);
+        ln_store<R, PRECISE, true>(h, sm, u_s, pre_off, a1, b1);
         publish_u();
         stamp();   // U1 published
         // token mix epilogue: x = x + silu(conv + bias)
         wait_acc();
         stamp();   // token-mix accumulator ready
-        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[n]); });
+        for_acc_tok<R>(taddr_tok, [&](int n, float v) { h[n] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[n]); });
         stamp();   // token-mix epilogue done
-        ln_stats<R>(h, sm, true);
-        stamp();   // LN2 stats done
-        ln_store<R, PRECISE>(h, sm, u_s, pre_off, a2, b2);
+        // channel-mix operand: normalised with the LN1 statistics; exact LN2 statistics follow while the GEMM runs
+        ln_store<R, PRECISE, false>(h, sm, u_s, pre_off, 0.f, 0.f);
         publish_u();
         stamp();   // U2 published
+        ln_stats<R, 1>(h, sm, true);
+        stamp();   // LN2 stats done (under the GEMM)
         // channel mix epilogue: x = x + silu(linear + bias)
         wait_acc();
         stamp();   // channel-mix accumulator ready
-        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] += silu_fast(v + bch); });
+        for_acc_cat<R, PRECISE>(taddr_cat, [&](int n, float v) {
+          const float2 r = gd[n];
+          h[n] += silu_fast(fmaf(r.x, v, fmaf(r.y, Sc, tc)));
+        });
+        drained(4);
         stamp();   // channel-mix epilogue done
       }
 
@@ -513,27 +656,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       wait_acc();
       if (warp * 32 < p.JD) {                    // warp-uniform: tcgen05.ld is .aligned
         // h is dead: reuse it for the head outputs (lane = output feature j, column = row)
-        for_acc<R>(lane_taddr, [&](int n, float v) { h[n] = v; });
+        for_acc_cat<R, PRECISE>(taddr_cat, [&](int n, float v) { h[n] = v; });
         if (c < p.JD && valid) {
           const float bo = p.w.b_out[c], sc = p.scale[b];
           const size_t base = ((size_t)b * p.JD + c) * LS_F;
-          const float* nzp = p.noise ? p.noise + (size_t)b * p.nsb + (size_t)c * p.nsj : nullptr;
-          const bool use_noise = (p.sp.mode != 2) && p.sp.add_noise && nzp != nullptr;
+          const float* nzp = io.noise ? io.noise + (size_t)b * io.nsb + (size_t)c * io.nsj : nullptr;
+          const bool use_noise = (sp.mode != 2) && sp.add_noise && nzp != nullptr;
 #pragma unroll
           for (int f = 0; f < LS_F; ++f) {
             const float oc = h[NPRE + f] + bo, ou = h[S + NPRE + f] + bo;
             float x0 = ou + sc * (oc - ou);                       // cfg_sampler.py:31
-            const float nz = use_noise ? nzp[(size_t)f * p.nsf] : 0.f;
+            const float nz = use_noise ? nzp[(size_t)f * io.nsf] : 0.f;
             float xp = 0.f;
-            x0 = ls_sampler_update(p.sp, x0, p.x_t[base + f], nz, &xp);
-            if (p.pred_x0) p.pred_x0[base + f] = x0;
-            if (p.sp.mode != 2) p.x_prev[base + f] = xp;
+            x0 = ls_sampler_update(sp, x0, __ldcg(x_t + base + f), nz, &xp);
+            if (io.pred_x0) io.pred_x0[base + f] = x0;
+            if (sp.mode != 2) io.x_prev[base + f] = xp;
           }
         }
       }
+      drained(p.MH);
       // the next tile's X operand overwrites U: every head MMA has completed (wait_acc above)
+      if (p.n_steps > 1) __threadfence();        // x_prev visible device-wide before the counter moves
       tc_fence_before_sync();
       epi_bar();
+      if (p.n_steps > 1 && valid && tid == 0) st_release_gpu(p.flags + b, k + 1);
     }
   }
   // ---- teardown ---------------------------------------------------------------------------
@@ -544,16 +690,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
 
 // ---- weight tape ------------------------------------------------------------------------------
 // stage = [128 x 64] block of W (rows m0.., cols k0..) as K-major swizzle-128B images, hi then lo.
+// kscale (or nullptr) multiplies column k: the channel-mix weights carry LayerNorm 2's alpha.
 __global__ void build_w_stage_kernel(const float* __restrict__ src, int rows, int cols, int ld, int m0, int k0,
-                                     uint8_t* __restrict__ dst) {
+                                     const float* __restrict__ kscale, uint8_t* __restrict__ dst) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 128 * 64; i += gridDim.x * blockDim.x) {
     const int m = i >> 6, k = i & 63;
-    const float v = (m0 + m < rows && k0 + k < cols) ? src[(size_t)(m0 + m) * ld + k0 + k] : 0.f;
+    float v = (m0 + m < rows && k0 + k < cols) ? src[(size_t)(m0 + m) * ld + k0 + k] : 0.f;
+    if (kscale != nullptr && k0 + k < cols) v = __fmul_rn(v, kscale[k0 + k]);
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
     const uint32_t off = tile_off(m, k, 0);
     *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
     *reinterpret_cast<__nv_bfloat16*>(dst + W_HALF + off) = lo;
+  }
+}
+
+// Per output channel c of a channel-mix layer (one warp each):
+//   Sc[c] = sum_k fl(W[c,k]*alpha[k]),  tc[c] = sum_k W[c,k]*beta[k] + bias[c]   (fp64 accumulation)
+__global__ void ch_fold_kernel(const float* __restrict__ w, const float* __restrict__ alpha, const float* __restrict__ beta,
+                               const float* __restrict__ bias, float* __restrict__ Sc, float* __restrict__ tc) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= LS_D) return;
+  double s = 0.0, t = 0.0;
+  for (int k = lane; k < LS_D; k += 32) {
+    const float wv = w[(size_t)c * LS_D + k];
+    s += (double)__fmul_rn(wv, alpha[k]);
+    t += (double)wv * (double)beta[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  if (lane == 0) {
+    Sc[c] = (float)s;
+    tc[c] = (float)(t + (double)bias[c]);
   }
 }
 
@@ -578,6 +749,9 @@ __global__ void build_wblk_kernel(const float* __restrict__ w_tok, const float* 
 struct FusedState {
   uint8_t* tape = nullptr;
   size_t tape_bytes = 0;
+  float* Sc = nullptr;     // [n_layers][512]
+  float* tc = nullptr;
+  int* flags = nullptr;    // [max_batch]
   int KIN = 0, MH = 0, n_stages = 0;
   int sm_count = 0;
   bool attr_done[2][2] = {{false, false}, {false, false}};
@@ -591,7 +765,8 @@ int launch_fused(ls_handle* h, FusedState* fs, const FusedParams& fp, cudaStream
     done = true;
   }
   // clusters of 2: an even grid, at most one CTA per SM
-  const int grid = (fp.B + 1 < fs->sm_count ? fp.B + 1 : fs->sm_count) & ~1;
+  const int items = fp.B * fp.n_steps;
+  const int grid = (items + 1 < fs->sm_count ? items + 1 : fs->sm_count) & ~1;
   fused_step_kernel<S, PRECISE><<<grid, NT_ALL, SMEM_DYN, s>>>(fp);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
@@ -605,6 +780,9 @@ void lsf_destroy(ls_handle* h) {
   if (h && h->fused) {
     FusedState* fs = static_cast<FusedState*>(h->fused);
     if (fs->tape) cudaFree(fs->tape);
+    if (fs->Sc) cudaFree(fs->Sc);
+    if (fs->tc) cudaFree(fs->tc);
+    if (fs->flags) cudaFree(fs->flags);
     delete fs;
     h->fused = nullptr;
   }
@@ -625,7 +803,13 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
     }
     fs->n_stages = 8 * fs->KIN + h->cfg.n_layers * 68 + 16 * fs->MH;
     fs->tape_bytes = (size_t)fs->n_stages * SLOT;
-    if (cudaMalloc(&fs->tape, fs->tape_bytes) != cudaSuccess) {
+    const size_t fold_bytes = (size_t)h->cfg.n_layers * LS_D * sizeof(float);
+    if (cudaMalloc(&fs->tape, fs->tape_bytes) != cudaSuccess || cudaMalloc(&fs->Sc, fold_bytes) != cudaSuccess ||
+        cudaMalloc(&fs->tc, fold_bytes) != cudaSuccess ||
+        cudaMalloc(&fs->flags, (size_t)h->cfg.max_batch * sizeof(int)) != cudaSuccess) {
+      if (fs->tape) cudaFree(fs->tape);
+      if (fs->Sc) cudaFree(fs->Sc);
+      if (fs->tc) cudaFree(fs->tc);
       delete fs;
       return ls_fail(h, LS_ENOMEM, "weight tape (%zu bytes)", (size_t)fs->n_stages * SLOT);
     }
@@ -643,7 +827,7 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
   const float* win = raw("input_mapping.weight");
   for (int mt = 0; mt < 4; ++mt)
     for (int kc = 0; kc < fs->KIN; ++kc) {
-      build_w_stage_kernel<<<16, 256, 0, s>>>(win, LS_D, h->JD, IN, mt * 128, kc * 64, fs->tape + st * SLOT);
+      build_w_stage_kernel<<<16, 256, 0, s>>>(win, LS_D, h->JD, IN, mt * 128, kc * 64, nullptr, fs->tape + st * SLOT);
       LS_LAUNCH_CHECK(h);
       st += 2;
     }
@@ -654,9 +838,12 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
     LS_LAUNCH_CHECK(h);
     st += 4;
     const float* wch = raw(p + "block2.1.weight");
+    const LsLayerW& L = h->w.layer[l];
+    ch_fold_kernel<<<LS_D / 8, 256, 0, s>>>(wch, L.ln2_a, L.ln2_b, L.b_ch, fs->Sc + (size_t)l * LS_D, fs->tc + (size_t)l * LS_D);
+    LS_LAUNCH_CHECK(h);
     for (int mt = 0; mt < 4; ++mt)
       for (int kc = 0; kc < 8; ++kc) {
-        build_w_stage_kernel<<<16, 256, 0, s>>>(wch, LS_D, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st * SLOT);
+        build_w_stage_kernel<<<16, 256, 0, s>>>(wch, LS_D, LS_D, LS_D, mt * 128, kc * 64, L.ln2_a, fs->tape + st * SLOT);
         LS_LAUNCH_CHECK(h);
         st += 2;
       }
@@ -664,7 +851,7 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
   const float* wout = raw("output_process.poseFinal.weight");
   for (int mt = 0; mt < fs->MH; ++mt)
     for (int kc = 0; kc < 8; ++kc) {
-      build_w_stage_kernel<<<16, 256, 0, s>>>(wout, h->JD, LS_D, LS_D, mt * 128, kc * 64, fs->tape + st * SLOT);
+      build_w_stage_kernel<<<16, 256, 0, s>>>(wout, h->JD, LS_D, LS_D, mt * 128, kc * 64, nullptr, fs->tape + st * SLOT);
       LS_LAUNCH_CHECK(h);
       st += 2;
     }
@@ -672,13 +859,22 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
   return LS_OK;
 }
 
-int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const float* x_t, const float* eps_c,
-             const float* eps_u, const float* noise, int64_t sb, int64_t sj, int64_t sf, const float* scale,
-             float* x_prev, float* pred_x0, cudaStream_t s) {
+// n_steps consecutive steps in one launch (n_steps <= LS_MAX_FUSED_STEPS).  Step k reads x from
+// x_in (k = 0) or io[k-1].x_prev, so with n_steps > 1 every step needs its own x_prev buffer.
+int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const ls_step_io* io, int precise,
+              const float* x_in, const float* scale, cudaStream_t s) {
   FusedState* fs = static_cast<FusedState*>(h->fused);
   if (!fs) return ls_fail(h, LS_EUNSUPPORTED, "tcgen05 path not available");
-  if (x_prev == x_t && p->mode != 2)
-    ;  // in-place update is fine: each element is read before it is written by the same thread
+  if (n_steps < 1 || n_steps > KMAX) return ls_fail(h, LS_EINVAL, "n_steps %d outside [1,%d]", n_steps, KMAX);
+  if (n_steps > 1 && B < 2) {
+    // With one clip the two CTAs of a cluster would hold consecutive steps of the SAME clip: the second waits
+    // for the first, which in turn needs its peer to drain the shared weight ring.  Run step by step.
+    for (int k = 0; k < n_steps; ++k) {
+      const int rc = lsf_steps(h, B, 1, p + k, io + k, precise, k == 0 ? x_in : io[k - 1].x_prev, scale, s);
+      if (rc != LS_OK) return rc;
+    }
+    return LS_OK;
+  }
   FusedParams fp{};
   fp.tape = fs->tape;
   fp.n_layers = h->cfg.n_layers;
@@ -686,12 +882,19 @@ int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const fl
   fp.KIN = fs->KIN;
   fp.MH = fs->MH;
   fp.B = B;
+  fp.n_steps = n_steps;
   fp.w = h->w;
+  fp.Sc = fs->Sc; fp.tc = fs->tc;
   fp.A = h->A; fp.P = h->P; fp.z_mu = h->z_mu; fp.z_lv = h->z_lv; fp.emo_tok = h->emo_tok;
-  fp.x_t = x_t; fp.eps_c = eps_c; fp.eps_u = eps_u; fp.noise = noise; fp.scale = scale;
-  fp.nsb = sb; fp.nsj = sj; fp.nsf = sf;
-  fp.x_prev = x_prev; fp.pred_x0 = pred_x0;
-  fp.sp = *p;
+  fp.x_in = x_in; fp.scale = scale;
+  fp.flags = fs->flags;
+  for (int k = 0; k < n_steps; ++k) {
+    fp.sp[k] = p[k];
+    fp.io[k].eps_c = io[k].eps_cond; fp.io[k].eps_u = io[k].eps_uncond; fp.io[k].noise = io[k].noise;
+    fp.io[k].nsb = io[k].noise_sb; fp.io[k].nsj = io[k].noise_sj; fp.io[k].nsf = io[k].noise_sf;
+    fp.io[k].x_prev = io[k].x_prev; fp.io[k].pred_x0 = io[k].pred_x0;
+  }
+  if (n_steps > 1) LS_CUDA(h, cudaMemsetAsync(fs->flags, 0, (size_t)B * sizeof(int), s));
   fp.timing = nullptr;
   static long long* tbuf = nullptr;
   const bool timing = getenv("LS_FUSED_TIMING") != nullptr;
@@ -707,8 +910,12 @@ int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const fl
     long long t[512];
     cudaStreamSynchronize(s);
     cudaMemcpy(t, tbuf, sizeof(t), cudaMemcpyDeviceToHost);
-    static const char* names[] = {"LN1 stats", "U1 publish", "tok acc wait", "tok epilogue", "LN2 stats", "U2 publish",
+    static const char* names[] = {"LN1 stats", "U1 publish", "tok acc wait", "tok epilogue", "U2 publish", "LN2 stats",
                                   "ch acc wait", "ch epilogue"};
+#if LS_MMA_PROF
+    fprintf(stderr, "[fused timing] MMA warp of CTA 0 over %lld rounds: total %lld cyc, waiting for weight stages %lld, "
+                    "waiting for operand tiles %lld\n", t[511], t[510], t[508], t[509]);
+#endif
     for (int w = 0; w < 2; ++w) {
       const long long* q = t + 256 * w;
       fprintf(stderr, "[fused timing] thread %d: X publish -> in-proj consumed %lld cyc\n", w ? 511 : 0, q[1] - q[0]);

@@ -120,6 +120,5 @@ int lsk_axpby(ls_handle* h, int64_t n, const float* a, const float* b, float ca,
 int lsf_init(ls_handle* h, cudaStream_t s);            // build bf16 weight tapes; 0 if available
 void lsf_destroy(ls_handle* h);
 int lsf_available(const ls_handle* h);
-int lsf_step(ls_handle* h, int B, const ls_step_params* p, int precise, const float* x_t, const float* eps_c,
-             const float* eps_u, const float* noise, int64_t sb, int64_t sj, int64_t sf, const float* scale,
-             float* x_prev, float* pred_x0, cudaStream_t s);
+int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const ls_step_io* io, int precise,
+              const float* x_in, const float* scale, cudaStream_t s);

@@ -151,6 +151,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Two 8-column loads (different column bases, same lanes) completed by ONE wait: the fused kernel's
+// channel-type accumulators keep the W_hi*U_lo and (W_hi+W_lo)*U_hi partial products in two column
+// ranges that the epilogue adds.
+__device__ __forceinline__ void tmem_ld8x2(uint32_t taddr_a, uint32_t taddr_b, float* a, float* b) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%16];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [%17];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr_a), "r"(taddr_b)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(r[8 + i]);
+  }
+}
+
 // ---- descriptors -------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit):
 //   [0,14)  matrix start address >> 4          [16,30) leading-dim byte offset >> 4

@@ -53,7 +53,7 @@ int main() {
   const int iters = 2048;
   for (int spread = 0; spread < 2; ++spread)
   for (int a_mn = 0; a_mn < 2; ++a_mn)
-    for (int N : {16, 48, 80, 128, 256}) {
+    for (int N : {16, 40, 48, 64, 80, 96, 112, 128, 144, 160, 192, 256}) {
       bench_kernel<<<1, 128, smem>>>(N, a_mn, iters, spread, d);
       long long c;
       if (cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { printf("error\n"); return 1; }

@@ -9,6 +9,9 @@
 //           (token-mix weights), M=128 N=80 K=80, LBO = channel-block stride, SBO = 1024
 //   case 3: as 2 with LBO / SBO swapped (to learn which reading of the ISA is right)
 //   case 4: case 0 with K split over two 64-channel blocks + accumulate flag (K=128)
+//   case 5: the concatenated operand of the fused kernel: B = 144 contiguous rows (lo image rows
+//           0..71 then hi image rows 0..71), one N=144 MMA per K step into D at column 152 (8- but not
+//           16-aligned), then N=80 MMAs from row 72 accumulating into D + 72 (column 224)
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,12 +59,19 @@ probe_kernel(int which, const __nv_bfloat16* __restrict__ u_g /*[80][128]*/, con
     uint8_t* dst = (k < 64) ? s.wt : s.wt2;
     *reinterpret_cast<__nv_bfloat16*>(dst + tile_off(n, k & 63, 0)) = v;
   }
+  if (which == 5) {       // 160 rows x 64 channels, one block: row r = u_g row (r % 80), channel c -> c + 64*(r / 80)
+    __syncthreads();
+    for (int i = tid; i < 160 * 64; i += 128) {
+      int r = i / 64, c = i % 64;
+      *reinterpret_cast<__nv_bfloat16*>(s.u + tile_off(r, c, 0)) = u_g[(r % 80) * NCH + c + 64 * (r / 80)];
+    }
+  }
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = s.tmem_base;
-  const uint32_t dcol = (which == 1) ? 80u : 0u;
+  const uint32_t dcol = (which == 1) ? 80u : (which == 5) ? 152u : 0u;
 
   if (tid == 0) {
     if (which == 0 || which == 1 || which == 4) {
@@ -77,6 +87,21 @@ probe_kernel(int which, const __nv_bfloat16* __restrict__ u_g /*[80][128]*/, con
           uint64_t bd = smem_desc(smem_u32(s.u) + b * CB_STRIDE + ks * 32, 16, 1024, SWZ_128B);
           umma_bf16(tmem + dcol, ad, bd, id, (b | ks) ? 1u : 0u);
         }
+    } else if (which == 5) {
+      mbar_arrive_expect_tx(&s.bar_w, 16384);
+      bulk_g2s(s.w, w_img, 16384, &s.bar_w);
+      mbar_wait(&s.bar_w, 0);
+      tc_fence_after_sync();
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        uint64_t ad = smem_desc(smem_u32(s.w) + ks * 32, 16, 1024, SWZ_128B);
+        uint64_t bd = smem_desc(smem_u32(s.u) + ks * 32, 16, 1024, SWZ_128B);
+        umma_bf16(tmem + dcol, ad, bd, idesc_bf16(128, 144, 0, 0), ks ? 1u : 0u);
+      }
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        uint64_t ad = smem_desc(smem_u32(s.w) + ks * 32, 16, 1024, SWZ_128B);
+        uint64_t bd = smem_desc(smem_u32(s.u) + 9 * 1024 + ks * 32, 16, 1024, SWZ_128B);
+        umma_bf16(tmem + dcol + 72, ad, bd, idesc_bf16(128, 80, 0, 0), 1u);
+      }
     } else {
       // token mix: D[ch][tok_out] = sum_tok_in U[tok_in][ch] * Wt[tok_out][tok_in]
       const uint32_t id = idesc_bf16(128, 80, 1, 0);
@@ -94,6 +119,13 @@ probe_kernel(int which, const __nv_bfloat16* __restrict__ u_g /*[80][128]*/, con
   mbar_wait(&s.bar_mma, 0);
   tc_fence_after_sync();
   // read back: warp w owns TMEM lanes 32w..32w+31 (= D rows)
+  if (which == 5) {
+    for (int c0 = 0; c0 < 144; c0 += 8) {
+      float v[8];
+      tmem_ld8(tmem + ((uint32_t)(warp * 32) << 16) + dcol + c0, v);
+      for (int i = 0; i < 8; ++i) d_out[(size_t)tid * 144 + c0 + i] = v[i];
+    }
+  } else
   for (int c0 = 0; c0 < 80; c0 += 16) {
     float v[16];
     tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + dcol + c0, v);
@@ -135,7 +167,7 @@ int main() {
   cudaMalloc(&dU, Ub.size() * 2);
   cudaMalloc(&dW, img.size());
   cudaMalloc(&dWT, WTb.size() * 2);
-  cudaMalloc(&dD, 128 * 80 * 4);
+  cudaMalloc(&dD, 128 * 144 * 4);
   cudaMemcpy(dU, Ub.data(), Ub.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dW, img.data(), img.size(), cudaMemcpyHostToDevice);
   cudaMemcpy(dWT, WTb.data(), WTb.size() * 2, cudaMemcpyHostToDevice);
@@ -170,6 +202,31 @@ int main() {
     printf("case %d: mismatches %d / %d, max err %g  (D[0][0..3] = %g %g %g %g)\n", which, bad, 128 * 80, maxerr, D[0],
            D[1], D[2], D[3]);
     if (which != 3) bad_total += bad;
+  }
+  {
+    cudaMemset(dD, 0xff, 128 * 144 * 4);
+    probe_kernel<<<1, 128, smem>>>(5, (const __nv_bfloat16*)dU, (const uint8_t*)dW, (const __nv_bfloat16*)dWT, dD);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      printf("case 5: CUDA error %s\n", cudaGetErrorString(e));
+      return 1;
+    }
+    std::vector<float> D(128 * 144);
+    cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+    int bad = 0;
+    double maxerr = 0;
+    auto urow = [&](int r, int k) { return U[(r % 80) * NCH + k + 64 * (r / 80)]; };
+    for (int m = 0; m < 128; ++m)
+      for (int n = 0; n < 144; ++n) {
+        double ref = 0;
+        for (int k = 0; k < 64; ++k) ref += (double)W[m * 128 + k] * urow(n, k);
+        if (n >= 72) ref *= 2;      // the N=80 product from row 72 lands on the same columns
+        double err = fabs(ref - D[m * 144 + n]);
+        if (!(err <= 1e-3)) ++bad;
+        if (err > maxerr || err != err) maxerr = err;
+      }
+    printf("case 5: mismatches %d / %d, max err %g\n", bad, 128 * 144, maxerr);
+    bad_total += bad;
   }
   printf(bad_total == 0 ? "PROBE OK\n" : "PROBE FAILED\n");
   return 0;

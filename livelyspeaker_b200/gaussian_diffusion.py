@@ -27,7 +27,7 @@ from copy import deepcopy
 import numpy as np
 import torch as th
 
-from ._cabi import LsStepParams
+from ._cabi import MAX_FUSED_STEPS, LsStepParams
 
 
 def get_named_beta_schedule(schedule_name, num_diffusion_timesteps, scale_betas=1.):
@@ -107,6 +107,10 @@ def _extract_into_tensor(arr, timesteps, broadcast_shape):
 
 
 class GaussianDiffusion:
+    # Loop iterations per launch on the fused route of the non-progressive loops (ls_step_multi);
+    # 1 = one launch per step.  The *_progressive generators always run step by step.
+    fused_chunk = MAX_FUSED_STEPS
+
     def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False,
                  lambda_rcxyz=0., lambda_vel=0., lambda_pose=1., lambda_orient=1., lambda_loc=1.,
                  data_rep='rot6d', lambda_root_vel=0., lambda_vel_rcxyz=0., lambda_fc=0.):
@@ -315,7 +319,7 @@ class GaussianDiffusion:
 
     def _sample_loop_progressive(self, ddim, model, shape, noise, clip_denoised, denoised_fn, cond_fn,
                                  model_kwargs, device, progress, eta, skip_timesteps, init_image,
-                                 randomize_class, cond_fn_with_grad, const_noise):
+                                 randomize_class, cond_fn_with_grad, const_noise, chunk=1):
         if cond_fn_with_grad:
             raise NotImplementedError("*_with_grad samplers are outside the sampling hot path (SURVEY.md 8f)")
         if device is None:
@@ -377,9 +381,38 @@ class GaussianDiffusion:
             if like.device != dev:
                 like = x_cur
             perm_like = th.empty(shape[3], B, shape[1], shape[2], device=dev).permute(1, 2, 3, 0)
+            chunk = max(1, min(int(chunk), MAX_FUSED_STEPS))
+            bar = None
             if progress:
                 from tqdm.auto import tqdm
-                indices = tqdm(indices)
+                if chunk > 1:
+                    bar = tqdm(total=len(indices))
+                else:
+                    indices = tqdm(indices)
+            k = 0
+            while chunk > 1 and k < len(indices):
+                # `chunk` loop iterations per launch (ls_step_multi).  The draws keep the reference's order
+                # (cond style, uncond style, step noise - per step), they are only made ahead of the launch.
+                idx = indices[k:k + chunk]
+                K = len(idx)
+                eps_c, eps_u, nzs = [], [], []
+                for j in range(K):
+                    eps_c.append(src.randn((B, 1, rag.latent_dim), dev))
+                    eps_u.append(src.randn((B, 1, rag.latent_dim), dev))
+                    nz = src.randn_like(like if k + j == 0 else perm_like)
+                    nzs.append(nz[[0]].expand(B, -1, -1, -1) if const_noise else nz)
+                xs = th.empty((K,) + tuple(x_cur.shape), device=dev)
+                x0s = th.empty_like(xs)
+                eng.step_multi([self.step_params(i, ddim=ddim, eta=eta, clip_denoised=clip_denoised) for i in idx],
+                               x_cur, eps_c, eps_u, nzs, scale, xs, x0s)
+                for j in range(K):
+                    yield {"sample": xs[j], "pred_xstart": x0s[j]}
+                x_cur = xs[K - 1]
+                k += K
+                if bar is not None:
+                    bar.update(K)
+            if chunk > 1:
+                return
             for k, i in enumerate(indices):
                 eps_c = src.randn((B, 1, rag.latent_dim), dev)
                 eps_u = src.randn((B, 1, rag.latent_dim), dev)
@@ -398,11 +431,11 @@ class GaussianDiffusion:
                       model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
                       randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False):
         final, dump = None, []
-        for i, sample in enumerate(self.p_sample_loop_progressive(
-                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
-                model_kwargs=model_kwargs, device=device, progress=progress, skip_timesteps=skip_timesteps,
-                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad,
-                const_noise=const_noise)):
+        # non-progressive loops run the fused route `fused_chunk` steps per launch (same draws, same results)
+        for i, sample in enumerate(self._sample_loop_progressive(
+                False, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress, 0.0,
+                skip_timesteps, init_image, randomize_class, cond_fn_with_grad, const_noise,
+                chunk=self.fused_chunk)):
             if dump_steps is not None and i in dump_steps:
                 dump.append(deepcopy(sample[self.dump_key]))
             final = sample
@@ -427,11 +460,10 @@ class GaussianDiffusion:
         if const_noise and not self.allow_ddim_const_noise:
             raise NotImplementedError()
         final = None
-        for sample in self.ddim_sample_loop_progressive(
-                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
-                model_kwargs=model_kwargs, device=device, progress=progress, eta=eta,
-                skip_timesteps=skip_timesteps, init_image=init_image, randomize_class=randomize_class,
-                cond_fn_with_grad=cond_fn_with_grad, const_noise=const_noise):
+        for sample in self._sample_loop_progressive(
+                True, model, shape, noise, clip_denoised, denoised_fn, cond_fn, model_kwargs, device, progress, eta,
+                skip_timesteps, init_image, randomize_class, cond_fn_with_grad, const_noise,
+                chunk=self.fused_chunk):
             final = sample
         return final["sample"]
 

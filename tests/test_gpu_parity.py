@@ -301,6 +301,36 @@ def test_full_size_properties_b512(impl):
     _close(outs[2.0], ou + 2 * (oc - ou), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("impl,B,K", [("auto", 3, 5), ("auto", 300, 7), ("auto", 512, 16), ("simt", 5, 3)])
+def test_multi_step_launch_equals_single_steps(impl, B, K):
+    """ls_step_multi (K loop iterations in one launch, (clip, step) items scheduled across the SMs with a
+    release/acquire counter per clip) must reproduce K ls_step calls bit for bit, x_prev and pred_x0 alike -
+    also when a clip's consecutive steps run on different SMs (B=300, 512: several rounds)."""
+    dims, sd, cfg, diffusion = build("ted", "", impl=impl)
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    eng = cfg.model.engine(B)
+    eng.set_cond(y, force=True)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 9, 3, 34, generator=g).to(DEV)
+    e_c = [torch.randn(B, 1, 512, generator=g).to(DEV) for _ in range(K)]
+    e_u = [torch.randn(B, 1, 512, generator=g).to(DEV) for _ in range(K)]
+    perm = torch.empty(34, B, 9, 3).permute(1, 2, 3, 0)
+    nz = [torch.randn(34, B, 9, 3, generator=g).permute(1, 2, 3, 0).to(DEV) for _ in range(K)]
+    assert nz[0].stride() == perm.stride()
+    params = [diffusion.step_params(i, ddim=(k % 2 == 1), eta=0.3, clip_denoised=False)
+              for k, i in enumerate(range(K - 1, -1, -1))]        # ends at i = 0 (no noise), mixes both samplers
+    xs, x0s = torch.empty(K, B, 9, 3, 34, device=DEV), torch.empty(K, B, 9, 3, 34, device=DEV)
+    eng.step_multi(params, x, e_c, e_u, nz, y["scale"], xs, x0s)
+    cur = x
+    for k in range(K):
+        nxt, x0 = torch.empty_like(x), torch.empty_like(x)
+        eng.step(params[k], cur, e_c[k], e_u[k], nz[k], y["scale"], nxt, x0)
+        assert torch.equal(nxt, xs[k]), "x_prev of step %d differs" % k
+        assert torch.equal(x0, x0s[k]), "pred_x0 of step %d differs" % k
+        cur = nxt
+    assert torch.isfinite(xs).all()
+
+
 def test_error_paths():
     from livelyspeaker_b200._cabi import LsError
     dims, sd, cfg, diffusion = build("ted", "ddim100")
@@ -325,3 +355,12 @@ def test_error_paths():
         eng.set_cond(y, force=True)
         eng.step(p, xg, torch.zeros(2, 1, 512, device=DEV), torch.zeros(2, 1, 512, device=DEV), xg, y["scale"],
                  torch.empty_like(xg), None)
+    ok = diffusion.step_params(5, ddim=True)
+    z = torch.zeros(2, 1, 512, device=DEV)
+    with pytest.raises(LsError):     # multi-step launch whose x_prev buffers alias
+        buf = torch.empty(1, 2, 9, 3, 34, device=DEV)
+        eng.step_multi([ok, ok], xg, [z, z], [z, z], [xg, xg], y["scale"], [buf[0], buf[0]], None)
+    with pytest.raises(LsError):     # more steps than LS_MAX_FUSED_STEPS
+        n = ls.MAX_FUSED_STEPS + 1
+        buf = torch.empty(n, 2, 9, 3, 34, device=DEV)
+        eng.step_multi([ok] * n, xg, [z] * n, [z] * n, [xg] * n, y["scale"], buf, None)

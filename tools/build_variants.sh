@@ -1,0 +1,20 @@
+#!/bin/bash
+# Diagnostic builds of libls_b200.so (selected at run time with LS_B200_LIB=<path>):
+#   libls_prof.so     MMA-warp cycle accounting (LS_FUSED_TIMING=1 prints it)
+#   libls_nomc.so     no cluster multicast: every CTA streams the whole weight tape from L2
+#   libls_nofetch.so  the producer signals stages without copying: pure MMA / epilogue timing, garbage results
+set -e
+cd "$(dirname "$0")/../livelyspeaker_b200/csrc"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+FLAGS="$ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr"
+make -j8 libls_b200.so > /dev/null
+build() {  # name, extra flags
+  $NVCC $FLAGS $2 -c ls_fused.cu -o /tmp/ls_fused_$1.o
+  $NVCC $ARCH -shared -o libls_$1.so ls_api.o ls_precompute.o ls_denoise_simt.o ls_update.o /tmp/ls_fused_$1.o
+}
+build prof "-DLS_MMA_PROF=1" &
+build nomc "-DLS_MULTICAST=0 -DLS_MMA_PROF=1" &
+build nofetch "-DLS_NOFETCH=1 -DLS_MMA_PROF=1" &
+wait
+ls -la libls_*.so
