@@ -13,8 +13,8 @@
 // All GEMMs run TRANSPOSED on the tensor cores, D^T[channel, row] = W[channel, k] * U^T[k, row]:
 //   M = 128 output channels (4 M-tiles for d = 512), N = rows of the tile, K = channels,
 // so the TMEM lane of an accumulator element is its CHANNEL and the column is its ROW:
-//   * each of the 512 epilogue threads owns one channel and keeps the fp32 residual stream
-//     h[row] of that channel in REGISTERS for the whole 8-layer stack;
+//   * each of the 512 epilogue threads keeps 4 channels x 18 rows of the fp32 residual stream
+//     in REGISTERS for the whole 8-layer stack;
 //   * TMEM holds only accumulators;
 //   * shared memory holds the bf16 operand tile U (LayerNorm output) - the very same bytes serve as
 //     the K-major B operand of the channel-mix GEMM and as the MN-major A operand of the token-mix
@@ -35,9 +35,10 @@
 // statistics - reduced while the GEMM runs - enter as a per-row scale / shift in the GEMM epilogue:
 //   W.(alpha*((h-mu)*rho)+beta)+b = (rho/s)*acc + ((m-mu)*rho)*S_c + t_c,  acc = (W.alpha)*((h-m)*s).
 //
-// Warp roles (20 warps): 0-15 epilogue (thread id == channel), 16 weight producer,
-// 17 MMA issuer + TMEM owner, 18-19 idle; warps 16-19 give most of their registers to the
-// epilogue warps with setmaxnreg so the 70-row residual stream fits without spilling.
+// Warp roles (20 warps): 0-15 epilogue, 16 weight producer, 17 MMA issuer + TMEM owner, 18-19 idle; warps
+// 16-19 give most of their registers to the epilogue warps with setmaxnreg (112 vs 32) so the residual stream fits.
+// Epilogue thread (lq = warp & 3, rq = warp >> 2, lane) owns TMEM lane 32 lq + lane of every M-tile (four
+// channels) and 18 of the 72 tile rows: see "epilogue thread mapping" below.
 #include <cuda_bf16.h>
 #include <cstdlib>
 
@@ -50,9 +51,13 @@ using namespace lstc;
 namespace {
 
 constexpr int NT_EPI = 512;
+// Register file: 16384 registers per SM sub-partition, 5 warps on each (20 warps).  Launch at 96 registers per
+// thread (5*32*96 = 15360 per sub-partition); setmaxnreg then moves them to the 4 epilogue warps of the
+// sub-partition: 4*32*112 + 32*32 == 15360.  18 warps at 112 do not launch ("too many resources": a
+// sub-partition would hold 5 warps * 3584), and a larger total blocks forever in setmaxnreg.inc.
 constexpr int NT_ALL = 640;                     // 16 epilogue warps + 1 producer + 1 MMA + 2 idle (register donors)
-constexpr int REGS_EPI = 112;                   // setmaxnreg budgets must conserve the launch allocation:
-constexpr int REGS_AUX = 32;                    // 512*112 + 128*32 == 640*96 (a larger total blocks forever in setmaxnreg.inc)
+constexpr int REGS_EPI = 112;
+constexpr int REGS_AUX = 32;
 constexpr int NROW = 80;                        // MMA N of a single-image product (rows of a tile, padded)
 constexpr int NCAT = 144;                       // MMA N of the concatenated [U_lo ; U_hi] operand
 constexpr int RGS = 9;                          // 8-row groups per image (72 rows)
@@ -85,11 +90,14 @@ constexpr int KMAX = LS_MAX_FUSED_STEPS;
 constexpr uint32_t OFF_U = 0;
 constexpr uint32_t OFF_PAD = U_BYTES;                   // 1024 zero bytes: row group 9 of the last hi image
 constexpr uint32_t OFF_RING = OFF_PAD + 1024;
-constexpr uint32_t OFF_PART = OFF_RING + NSLOT * SLOT;  // [16 warps][72 rows] float2 LN partial sums
-constexpr uint32_t OFF_STATS = OFF_PART + 16 * 72 * 8;  // [72] float2 (mean, rstd)
-constexpr uint32_t OFF_GD = OFF_STATS + 72 * 8;         // [72] float2 channel-mix epilogue (row scale, row shift)
+constexpr uint32_t OFF_PART = OFF_RING + NSLOT * SLOT;  // [16 warps][18 rows] float2 LN partial sums
+constexpr uint32_t OFF_STATS = OFF_PART + 16 * 18 * 8;  // [72] float2 (rstd, -mean * rstd)
+constexpr uint32_t OFF_MEAN = OFF_STATS + 72 * 8;       // [72] float mean (the next statistics' shift)
+constexpr uint32_t OFF_GD = OFF_MEAN + 72 * 4;          // [72] float2 channel-mix epilogue (row scale, row shift)
 constexpr uint32_t OFF_BTOK = OFF_GD + 72 * 8;          // [72] float token-mix bias
-constexpr uint32_t OFF_BARS = OFF_BTOK + 72 * 4;        // mbarriers
+constexpr uint32_t OFF_PAB = OFF_BTOK + 72 * 4;         // [512] float2 (ln1 alpha, beta) of the current layer, thread-private slots
+constexpr uint32_t OFF_EMB = OFF_PAB + 512 * 8;         // [512] float time embedding of the current item, thread-private slots
+constexpr uint32_t OFF_BARS = OFF_EMB + 512 * 4;         // mbarriers
 constexpr uint32_t OFF_TMEM = OFF_BARS + 24 * 8;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_DYN = SMEM_USED + 1024;         // + alignment slack
@@ -132,8 +140,11 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// No "memory" clobber: the operand tile is written only through these stores and read only by the async proxy
+// (after fence.proxy.async, itself a volatile asm that stays behind them), so the compiler may hoist the shared
+// loads of the next row pair above the stores of this one instead of serialising pair after pair.
 __device__ __forceinline__ void sts_u16(uint32_t saddr, uint16_t v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v) : "memory");
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(saddr), "h"(v));
 }
 // hi/lo bf16 split of v, stored at byte offset `off` of the lo image (hi image = + HI_OFF); u_s = shared-space address of U
 template <bool PRECISE>
@@ -168,118 +179,175 @@ __device__ __forceinline__ uint32_t row_off(uint32_t pre_off, int n) {
   return (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
 }
 
-// Per-row (sum, sum of squares) over the 512 channels.  h[] holds this thread's channel; `shift` rows
-// come from the previous stats (robust single-pass variance), or 0 when use_shift is false.
-//   CORR == 0: stats[row] = (mean, 1/std).
-//   CORR == 1: (m, s) = stats[row] is what the operand tile was normalised with; the exact (mu, rho)
-//              give the channel-mix epilogue's gd[row] = (rho / s, (m - mu) * rho) and replace stats[row].
-template <int R, int CORR>
-__device__ __forceinline__ void ln_stats(const float (&h)[72], uint8_t* sm, bool use_shift) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float2* part = reinterpret_cast<float2*>(sm + OFF_PART);
-  float2* stats = reinterpret_cast<float2*>(sm + OFF_STATS);
+// ---- epilogue thread mapping ---------------------------------------------------------------------
+// Thread (lq = warp & 3, rq = warp >> 2, lane) owns TMEM lane 32*lq + lane of EVERY M-tile, i.e. the four
+// channels c_m = 128*m + 32*lq + lane, and the NQ = 18 tile rows [18*rq, 18*rq + 18).  So
+//   * every accumulator is drained by all 16 warps (18 columns each) as soon as its M-tile completes - the
+//     tail after the last M-tile of a GEMM is a quarter of what a warp-per-M-tile mapping leaves;
+//   * a LayerNorm row lives in ONE group of 4 warps (rq): 4 local adds, a 38-shuffle transposing butterfly,
+//     a 4-way exchange through shared memory and two 128-thread named barriers - no CTA-wide barrier.
+constexpr int NQ = 18;
+
+__device__ __forceinline__ void group_bar(int rq) { asm volatile("bar.sync %0, 128;" ::"r"(2 + rq) : "memory"); }
+
+// transposing butterfly: V values per lane in, the sum over all 32 lanes of value idx(lane) out in v[0]
+template <int V>
+__device__ __forceinline__ void butterfly(float* v, int lane) {
 #pragma unroll
-  for (int g = 0; g < 9; ++g) {
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int n = 8 * g + j;
-      float d = 0.f;
-      if (n < R) d = h[n] - (use_shift ? stats[n].x : 0.f);
-      s[j] = d;
-      q[j] = d * d;
-    }
-    // halving butterfly: after the three steps lane bits (4,3,2) select the row
-#pragma unroll
-    for (int step = 0; step < 3; ++step) {
-      const int half = 4 >> step;            // 4, 2, 1 values kept
-      const int xm = 16 >> step;             // xor 16, 8, 4
+  for (int s = 0; s < 5; ++s) {
+    const int xm = 16 >> s, half = (V >> 1) >> s;
+    if (half >= 1) {
       const bool up = (lane & xm) != 0;
 #pragma unroll
       for (int j = 0; j < half; ++j) {
-        const float send_s = up ? s[j] : s[j + half];
-        const float send_q = up ? q[j] : q[j + half];
-        const float keep_s = up ? s[j + half] : s[j];
-        const float keep_q = up ? q[j + half] : q[j];
-        s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, xm);
-        q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, xm);
+        const float send = up ? v[j] : v[j + half];
+        const float keep = up ? v[j + half] : v[j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, send, xm);
       }
-    }
-    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 2);
-    q[0] += __shfl_xor_sync(0xffffffffu, q[0], 2);
-    s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
-    q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
-    if ((lane & 3) == 0) {
-      const int row = 8 * g + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-      part[warp * 72 + row] = make_float2(s[0], q[0]);
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], xm);
     }
   }
-  epi_bar();
-  if (tid < R) {              // 70 threads in parallel, 16 pipelined loads each (a warp-shuffle finish was slower)
+}
+
+// Per-row (sum, sum of squares) over the 512 channels of this group's 18 rows.  `shift` = the previous mean of
+// the row (robust single-pass variance), or 0 when use_shift is false.
+//   CORR == 0: stats[row] = (rstd, -mean * rstd) (normalisation is one FMA), means[row] = mean.
+//   CORR == 1: (m, s) = the mean / rstd the operand tile was normalised with; the exact (mu, rho)
+//              give the channel-mix epilogue's gd[row] = (rho / s, (m - mu) * rho) and replace stats / means.
+template <int CORR>
+__device__ __forceinline__ void ln_stats_q(const float (&h)[72], uint8_t* sm, int rq, bool use_shift) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* part = reinterpret_cast<float*>(sm + OFF_PART);          // [16 warps][18 rows][2]
+  float2* stats = reinterpret_cast<float2*>(sm + OFF_STATS);
+  float* means = reinterpret_cast<float*>(sm + OFF_MEAN);
+  const int r0 = NQ * rq;
+  auto row_sq = [&](int j, float& s, float& q) {
+    const float sh = use_shift ? means[r0 + j] : 0.f;
+    const float d0 = h[j] - sh, d1 = h[NQ + j] - sh, d2 = h[2 * NQ + j] - sh, d3 = h[3 * NQ + j] - sh;
+    s = (d0 + d1) + (d2 + d3);
+    q = fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+  };
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {          // rows 8g .. 8g+7: values 0..7 = sums, 8..15 = sums of squares
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) row_sq(8 * g + i, v[i], v[8 + i]);
+    butterfly<16>(v, lane);              // lane bits (4 | 3,2,1) select (q? | row)
+    if ((lane & 1) == 0) part[((warp * NQ) + 8 * g + ((lane >> 1) & 7)) * 2 + (lane >> 4)] = v[0];
+  }
+  {                                      // rows 16, 17
+    float v[4];
+    row_sq(16, v[0], v[2]);
+    row_sq(17, v[1], v[3]);
+    butterfly<4>(v, lane);               // lane bits (4 | 3) select (q? | row)
+    if ((lane & 7) == 0) part[((warp * NQ) + 16 + ((lane >> 3) & 1)) * 2 + (lane >> 4)] = v[0];
+  }
+  group_bar(rq);
+  const int j = tid & 127;
+  if (j < NQ) {
     float ss = 0.f, qq = 0.f;
 #pragma unroll
-    for (int w = 0; w < 16; ++w) {
-      const float2 p = part[w * 72 + tid];
-      ss += p.x;
-      qq += p.y;
+    for (int w = 0; w < 4; ++w) {
+      const float2 pr = *reinterpret_cast<const float2*>(part + (((4 * rq + w) * NQ) + j) * 2);
+      ss += pr.x;
+      qq += pr.y;
     }
-    const float2 old = stats[tid];
-    const float sh = use_shift ? old.x : 0.f;
+    const float old_mean = means[r0 + j], old_rstd = stats[r0 + j].x;
+    const float sh = use_shift ? old_mean : 0.f;
     const float md = ss * (1.f / 512.f);
     const float var = fmaxf(qq * (1.f / 512.f) - md * md, 0.f);
     const float mu = sh + md, rho = rsqrtf(var + 1e-5f);
     if (CORR) {
       float2* gd = reinterpret_cast<float2*>(sm + OFF_GD);
-      gd[tid] = make_float2(__fdividef(rho, old.y), (old.x - mu) * rho);
+      gd[r0 + j] = make_float2(__fdividef(rho, old_rstd), (old_mean - mu) * rho);
     }
-    stats[tid] = make_float2(mu, rho);
+    stats[r0 + j] = make_float2(rho, -mu * rho);
+    means[r0 + j] = mu;
   }
-  epi_bar();
+  group_bar(rq);
 }
 
-// LayerNorm of h -> bf16 (hi, lo) operand tile.  pre = offset of (row 0, channel c) in the lo image
-// with the chunk bits at [4,7): row n lives at (pre ^ ((n&7)<<4)) + (n&7)*128 + (n>>3)*1024.
-// AFFINE: (h - mean) * rstd * alpha + beta (LayerNorm 1).  !AFFINE: (h - mean) * rstd only (the
-// provisional normalisation of the channel-mix operand; alpha/beta live in the tape / epilogue).
-template <int R, bool PRECISE, bool AFFINE>
-__device__ __forceinline__ void ln_store(const float (&h)[72], uint8_t* sm, uint32_t u_s, uint32_t pre_off, float alpha,
-                                         float beta) {
-  const float2* stats = reinterpret_cast<const float2*>(sm + OFF_STATS);
-  static_assert(R % 2 == 0, "rows are stored in pairs");
+// One channel's 18 rows -> bf16 (hi, lo) operand tile.  Row p = 18*rq + j of a channel lives at
+// (pre ^ ((p & 7) << 4)) + 128 * p in the lo image (pre = channel part of the offset, swizzle chunk at bits [4,7)).
+// With p & 7 = (2*rq + j) & 7 and 2*rq even, rows j and j^1 differ by bit 4, rows j and j^4 by bit 6, so two
+// per-thread bases (y0: j = 0, y2: j = 2) reach every row with one XOR by a constant and an immediate offset.
+__device__ __forceinline__ uint32_t row_addr(uint32_t y0, uint32_t y2, int j) {
+  const int i = j & 7;
+  const uint32_t yb = (i & 2) ? y2 : y0;
+  const uint32_t x = (uint32_t)(((i & 1) << 4) | (((i >> 2) & 1) << 6));
+  return (x ? (yb ^ x) : yb) + 128u * (uint32_t)((i & 1) + 4 * ((i >> 2) & 1)) + 128u * (uint32_t)(j - i);
+}
+//   MODE 0: (h - mean) * rstd * alpha + beta (LayerNorm 1)
+//   MODE 1: (h - mean) * rstd               (provisional normalisation of the channel-mix operand)
+//   MODE 2: h                               (output head operand)
+template <bool PRECISE, int MODE>
+__device__ __forceinline__ void store_rows(const float* hm, const float2* st, uint32_t u_s, uint32_t y0, uint32_t y2,
+                                           uint32_t ch_off, bool ok_tail, float alpha, float beta) {
+  // Two row pairs per iteration with all shared LOADS ahead of the shared STORES: ptxas cannot prove that the
+  // statistics do not alias the operand tile, so a load placed after a store waits for it and the 20-instruction
+  // chains of consecutive pairs would run back to back instead of overlapping.
+  auto norm = [&](float v, float rstd, float nmr) {       // nmr = -mean * rstd
+    if (MODE == 2) return v;
+    const float u = fmaf(v, rstd, nmr);
+    return MODE == 0 ? fmaf(u, alpha, beta) : u;
+  };
 #pragma unroll
-  for (int n = 0; n < R; n += 2) {
-    const float2 s0 = stats[n], s1 = stats[n + 1];
-    float u0 = (h[n] - s0.x) * s0.y, u1 = (h[n + 1] - s1.x) * s1.y;
-    if (AFFINE) {
-      u0 = fmaf(u0, alpha, beta);
-      u1 = fmaf(u1, alpha, beta);
+  for (int j = 0; j < NQ; j += 4) {
+    const bool two = (j + 2 < NQ);
+    float4 sa = make_float4(0.f, 1.f, 0.f, 1.f), sb = sa;
+    if (MODE != 2) {
+      sa = *reinterpret_cast<const float4*>(st + j);                 // (rstd, -mean*rstd) of rows j, j+1
+      if (two) sb = *reinterpret_cast<const float4*>(st + j + 2);
     }
-    store_split2<PRECISE>(u_s, row_off(pre_off, n), row_off(pre_off, n + 1), u0, u1);
+    const float a0 = norm(hm[j], sa.x, sa.y), a1 = norm(hm[j + 1], sa.z, sa.w);
+    float b0 = 0.f, b1 = 0.f;
+    if (two) {
+      b0 = norm(hm[j + 2], sb.x, sb.y);
+      b1 = norm(hm[j + 3], sb.z, sb.w);
+    }
+    if (j < 16 || ok_tail) store_split2<PRECISE>(u_s, row_addr(y0, y2, j) + ch_off, row_addr(y0, y2, j + 1) + ch_off, a0, a1);
+    if (two && (j + 2 < 16 || ok_tail))
+      store_split2<PRECISE>(u_s, row_addr(y0, y2, j + 2) + ch_off, row_addr(y0, y2, j + 3) + ch_off, b0, b1);
   }
 }
 
-// Walk the token-mix accumulator columns [0, R) of this thread's TMEM lane in chunks of 16 (+8) and hand
-// (row, value) to f with compile-time row indices.  Must be executed by whole warps.
-template <int R, class F>
-__device__ __forceinline__ void for_acc_tok(uint32_t taddr, F&& f) {
+// This thread's 18 columns [taddr, taddr + 18) of one accumulator (CAT: plus the columns 72 further that hold
+// the other partial product) handed to f(j, value) with compile-time j.  Whole warps only.
+template <bool CAT, class F>
+__device__ __forceinline__ void acc_rows(uint32_t taddr, F&& f) {
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    float v[16];
-    tmem_ld16(taddr + c0, v);
+  for (int c0 = 0; c0 < 16; c0 += 8) {
+    float a[8], b[8];
+    if (CAT) {
+      tmem_ld8x2(taddr + c0, taddr + CAT_HI + c0, a, b);
+    } else {
+      tmem_ld8(taddr + c0, a);
 #pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (c0 + j < R) f(c0 + j, v[j]);
+      for (int i = 0; i < 8; ++i) b[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f(c0 + i, a[i] + b[i]);
   }
-  {
-    float v[8];
-    tmem_ld8(taddr + 64, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (64 + j < R) f(64 + j, v[j]);
-  }
+  float a[2], b[2] = {0.f, 0.f};
+  if (CAT) tmem_ld2x2(taddr + 16, taddr + CAT_HI + 16, a, b);
+  else tmem_ld2(taddr + 16, a);
+  f(16, a[0] + b[0]);
+  f(17, a[1] + b[1]);
 }
 
-// Same for a channel-type accumulator buffer: value(row) = D[row] (W_hi*U_lo) + D[72 + row] (the rest).
+// Token-mix accumulator: the 18 columns in ONE load round (16 + 2, a single wait).
+template <class F>
+__device__ __forceinline__ void acc_rows_tok(uint32_t taddr, F&& f) {
+  float a[16], b[2];
+  tmem_ld16p2(taddr, a, b);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f(i, a[i]);
+  f(16, b[0]);
+  f(17, b[1]);
+}
+
+// The head reads whole accumulator rows (lane = output feature): columns [0, R) of a channel-type buffer.
 template <int R, bool PRECISE, class F>
 __device__ __forceinline__ void for_acc_cat(uint32_t taddr, F&& f) {
 #pragma unroll
@@ -310,7 +378,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
   constexpr int NPRE = S - LS_F;      // prefix tokens per pass
   static_assert(R <= 72, "tile rows");
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-aligned base by POINTER arithmetic on the __shared__ array: an integer round trip would hide the address
+  // space from the compiler and turn every shared access below into a generic LD / ST
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BARS);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_TMEM);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -323,10 +393,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       mbar_init(&bars[BAR_EMPTY0 + s], LS_MULTICAST ? 2 : 1);   // multicast: the MMA issuers of BOTH CTAs release a slot
     }
     for (int m = 0; m < 4; ++m) {
-      mbar_init(&bars[BAR_UREADY0 + m], 128);     // the 4 warps that own the channels of M-tile m
+      mbar_init(&bars[BAR_UREADY0 + m], NT_EPI);  // every epilogue thread writes 18 rows of one channel of M-tile m
       mbar_init(&bars[BAR_ACC0 + m], 1);
     }
-    mbar_init(&bars[BAR_DRAIN], 128);             // M-tile 0's warps have read accumulator buffer 0 (M-tile 3 reuses it)
+    mbar_init(&bars[BAR_DRAIN], NT_EPI);          // accumulator buffer 0 has been read (M-tile 3 reuses it)
     mbar_fence_init();
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
@@ -528,35 +598,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
    }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
-    // ================= epilogue: thread == channel ==========================================
-    const int c = tid;
-    const int mt = warp >> 2;
-    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t taddr_tok = lane_base + (uint32_t)mt * NROW;
-    const uint32_t taddr_cat = lane_base + (uint32_t)(mt % NACC) * ACC_COLS;
-    const uint32_t pre_off = (uint32_t)(c >> 6) * CBS + (uint32_t)(((c & 63) >> 3) << 4) + (uint32_t)(c & 7) * 2u;
+    // ================= epilogue: thread == (TMEM lane, row quarter) ============================
+    const int lq = warp & 3, rq = warp >> 2;
+    const int r0 = NQ * rq;                       // first tile row of this thread
+    const bool ok_tail = (R == 72) || (rq != 3);  // rows r0+16, r0+17 exist (TED: the last quarter has 16 rows)
+    const int c0 = 32 * lq + lane;                // channel of M-tile 0; M-tile m adds 128*m
+    const uint32_t lane_base = tmem + ((uint32_t)(lq * 32) << 16);
     float* btok_s = reinterpret_cast<float*>(sm + OFF_BTOK);
-    const float2* gd = reinterpret_cast<const float2*>(sm + OFF_GD);
+    float* emb_s = reinterpret_cast<float*>(sm + OFF_EMB);
+    float2* pab_s = reinterpret_cast<float2*>(sm + OFF_PAB);
+    const float2* stats_q = reinterpret_cast<const float2*>(sm + OFF_STATS) + r0;
+    const float2* gd_q = reinterpret_cast<const float2*>(sm + OFF_GD) + r0;
     const uint32_t u_s = smem_u32(sm + OFF_U);
+    uint32_t y0, y2;                              // see row_addr
+    {
+      const uint32_t pre = (uint32_t)(c0 >> 6) * CBS + (uint32_t)(((c0 & 63) >> 3) << 4) + (uint32_t)(c0 & 7) * 2u;
+      y0 = (pre ^ ((uint32_t)((2 * rq) & 7) << 4)) + 128u * (uint32_t)r0;
+      y2 = (pre ^ ((uint32_t)((2 * rq + 2) & 7) << 4)) + 128u * (uint32_t)(r0 + 2);
+    }
     uint32_t aphase = 0;
-    auto wait_acc = [&]() {
-      mbar_wait(&bars[BAR_ACC0 + mt], aphase & 1);
-      ++aphase;
+    auto wait_acc = [&](int m) {
+      mbar_wait(&bars[BAR_ACC0 + m], aphase & 1);
       __syncwarp();                 // the spin loop may leave the warp diverged; tcgen05.ld is .aligned
       tc_fence_after_sync();
     };
-    auto publish_u = [&]() {        // operand tile written (and accumulators consumed)
+    auto publish_u = [&](int m) {   // this thread's part of the operand channels of M-tile m is written
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&bars[BAR_UREADY0 + mt]);
+      mbar_arrive(&bars[BAR_UREADY0 + m]);
     };
-    auto drained = [&](int n_mt) {  // accumulator buffer 0 read: M-tile 3 of the same GEMM may overwrite it
-      if (n_mt > NACC && mt == 0) {
-        tc_fence_before_sync();
-        mbar_arrive(&bars[BAR_DRAIN]);
-      }
+    auto drained = [&]() {          // this thread's part of accumulator buffer 0 is read (M-tile 3 reuses it)
+      tc_fence_before_sync();
+      mbar_arrive(&bars[BAR_DRAIN]);
     };
-    float h[72];
+    float h[72];                    // h[m * 18 + j]: channel c0 + 128 m, row r0 + j
     int tix = 0;
 
     for (int round = 0; round < n_rounds; ++round) {
@@ -576,7 +651,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           while (ld_acquire_gpu(p.flags + b) < k) __nanosleep(64);
         epi_bar();
       }
-      const float emb = p.w.emb_table[(size_t)sp.t_model * LS_D + c];
+      // Per-channel parameters used on the critical path (time embedding, LayerNorm-1 alpha / beta) are parked
+      // in thread-private shared-memory slots: with 219 KB of shared memory the L1 left over is too small to
+      // keep them, and an L2 round trip per M-tile inside the operand stores costs more than the stores.
+      {
+        float er[4];
+        float2 ab[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          er[m] = p.w.emb_table[(size_t)sp.t_model * LS_D + c0 + 128 * m];
+          ab[m] = make_float2(p.w.layer[0].ln1_a[c0 + 128 * m], p.w.layer[0].ln1_b[c0 + 128 * m]);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          emb_s[c0 + 128 * m] = er[m];
+          pab_s[c0 + 128 * m] = ab[m];
+        }
+      }
       // ---- X operand: x_t[b] (hi, lo) into rows p*S + NPRE + f, k = j ----------------------
       const float* xb = x_t + (size_t)b * p.JD * LS_F;
       for (int i = tid; i < p.JD * LS_F; i += NT_EPI) {
@@ -585,78 +676,117 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         store_split<PRECISE>(u_s, tile_off(NPRE + f, j, CBS), v);
         store_split<PRECISE>(u_s, tile_off(S + NPRE + f, j, CBS), v);
       }
-      publish_u();
+#pragma unroll
+      for (int m = 0; m < 4; ++m) publish_u(m);
       stamp();   // 0: X operand published
       // ---- residual stream init: hoisted terms now, projection result when it lands --------
-      {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int c = c0 + 128 * m;
         const float mu = p.z_mu[(size_t)b * LS_D + c], sd = __expf(0.5f * p.z_lv[(size_t)b * LS_D + c]);
-        h[0] = fmaf(io.eps_c[(size_t)b * LS_D + c], sd, mu);
-        h[S] = fmaf(io.eps_u[(size_t)b * LS_D + c], sd, mu);
-        if (NPRE == 2) h[1] = h[S + 1] = p.emo_tok[(size_t)b * LS_D + c];
+        const float st_c = fmaf(io.eps_c[(size_t)b * LS_D + c], sd, mu), st_u = fmaf(io.eps_u[(size_t)b * LS_D + c], sd, mu);
+        const float emo = (NPRE == 2) ? p.emo_tok[(size_t)b * LS_D + c] : 0.f;
         const float* Pb = p.P + (size_t)b * LS_F * LS_D + c;
         const float* Ab = p.A + (size_t)b * LS_F * LS_D + c;
 #pragma unroll
-        for (int f = 0; f < LS_F; ++f) {
-          const float pv = Pb[f * LS_D];
-          h[S + NPRE + f] = pv;
-          h[NPRE + f] = pv + Ab[f * LS_D];
+        for (int j = 0; j < NQ; ++j) {          // branch-free: the loads of all rows are in flight together
+          const int n = r0 + j;
+          const bool unc = n >= S;
+          const int tok = unc ? n - S : n;
+          const int f = min(max(tok - NPRE, 0), LS_F - 1);
+          const float pv = Pb[f * LS_D], av = Ab[f * LS_D];
+          float v = unc ? pv : pv + av;
+          if (NPRE == 2 && tok == 1) v = emo;
+          if (tok == 0) v = unc ? st_u : st_c;
+          h[m * NQ + j] = (n < R) ? v : 0.f;
         }
       }
-      wait_acc();
-      for_acc_cat<R, PRECISE>(taddr_cat, [&](int n, float v) {
-        if ((n % S) >= NPRE) h[n] += v;          // prefix-token rows keep their direct values
-      });
-      drained(4);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        wait_acc(m);
+        acc_rows<PRECISE>(lane_base + (uint32_t)((m % NACC) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
+                          [&](int j, float v) {
+          const int n = r0 + j, tok = n >= S ? n - S : n;
+          if (tok >= NPRE && n < R) h[m * NQ + j] += v;          // prefix-token rows keep their direct values
+        });
+        if (m == 0) drained();
+      }
+      ++aphase;
       stamp();   // 1: input projection consumed
 
       for (int l = 0; l < p.n_layers; ++l) {
         const LsLayerW L = p.w.layer[l];
-        const float a1 = L.ln1_a[c], b1 = L.ln1_b[c];
-        const float Sc = p.Sc[l * LS_D + c], tc = p.tc[l * LS_D + c];
         if (!TokBias<S>::kInGemm && tid < S) btok_s[tid] = btok_s[S + tid] = L.b_tok[tid];
         // x = x + emb ; LN1 ; -> operand tile
 #pragma unroll
-        for (int n = 0; n < R; ++n) h[n] += emb;
-        if (l == 0) ln_stats<R, 0>(h, sm, false);     // provisional means for the shift
-        ln_stats<R, 0>(h, sm, true);
+        for (int m = 0; m < 4; ++m) {
+          const float emb = emb_s[c0 + 128 * m];
+#pragma unroll
+          for (int j = 0; j < NQ; ++j) h[m * NQ + j] += emb;
+        }
+        if (l == 0) ln_stats_q<0>(h, sm, rq, false);     // provisional means for the shift
+        ln_stats_q<0>(h, sm, rq, true);
         stamp();   // LN1 stats done
-        ln_store<R, PRECISE, true>(h, sm, u_s, pre_off, a1, b1);
-        publish_u();
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float2 ab = pab_s[c0 + 128 * m];
+          store_rows<PRECISE, 0>(h + m * NQ, stats_q, u_s, y0, y2, (uint32_t)(2 * m) * CBS, ok_tail, ab.x, ab.y);
+          publish_u(m);
+        }
         stamp();   // U1 published
-        // token mix epilogue: x = x + silu(conv + bias)
-        wait_acc();
-        stamp();   // token-mix accumulator ready
-        for_acc_tok<R>(taddr_tok, [&](int n, float v) { h[n] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[n]); });
-        stamp();   // token-mix epilogue done
-        // channel-mix operand: normalised with the LN1 statistics; exact LN2 statistics follow while the GEMM runs
-        ln_store<R, PRECISE, false>(h, sm, u_s, pre_off, 0.f, 0.f);
-        publish_u();
-        stamp();   // U2 published
-        ln_stats<R, 1>(h, sm, true);
+        // token mix epilogue x = x + silu(conv + bias), then straight into the channel-mix operand:
+        // normalised with the LN1 statistics; the exact LN2 statistics follow while the GEMM runs
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          wait_acc(m);
+          acc_rows_tok(lane_base + (uint32_t)(m * NROW + r0), [&](int j, float v) {
+            if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[r0 + j]);
+          });
+          store_rows<PRECISE, 1>(h + m * NQ, stats_q, u_s, y0, y2, (uint32_t)(2 * m) * CBS, ok_tail, 0.f, 0.f);
+          publish_u(m);
+        }
+        ++aphase;
+        stamp();   // token-mix epilogue done, U2 published
+        ln_stats_q<1>(h, sm, rq, true);
+        if (l + 1 < p.n_layers) {     // next layer's LayerNorm-1 parameters; the L2 latency disappears in the wait below
+          const LsLayerW& Ln = p.w.layer[l + 1];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) pab_s[c0 + 128 * m] = make_float2(Ln.ln1_a[c0 + 128 * m], Ln.ln1_b[c0 + 128 * m]);
+        }
         stamp();   // LN2 stats done (under the GEMM)
         // channel mix epilogue: x = x + silu(linear + bias)
-        wait_acc();
-        stamp();   // channel-mix accumulator ready
-        for_acc_cat<R, PRECISE>(taddr_cat, [&](int n, float v) {
-          const float2 r = gd[n];
-          h[n] += silu_fast(fmaf(r.x, v, fmaf(r.y, Sc, tc)));
-        });
-        drained(4);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float Sc = p.Sc[l * LS_D + c0 + 128 * m], tc = p.tc[l * LS_D + c0 + 128 * m];
+          wait_acc(m);
+          if (m == 0) stamp();   // first channel-mix accumulator ready
+          acc_rows<PRECISE>(lane_base + (uint32_t)((m % NACC) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
+                            [&](int j, float v) {
+            const float2 r = gd_q[j];
+            if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(fmaf(r.x, v, fmaf(r.y, Sc, tc)));
+          });
+          if (m == 0) drained();
+          if (m == 2) stamp();   // three of four M-tiles consumed
+        }
+        ++aphase;
         stamp();   // channel-mix epilogue done
       }
 
       // ---- output head operand: plain hi/lo split of h -------------------------------------
-      // Every thread must be past its last wait_acc before U is overwritten: the channel-mix
-      // MMAs of the other M-tiles still read U until their own accumulator barrier fires.
-      epi_bar();
+      // This thread has waited for every M-tile of the last channel mix, so all MMAs reading U are complete.
 #pragma unroll
-      for (int n = 0; n < R; n += 2)
-        store_split2<PRECISE>(u_s, row_off(pre_off, n), row_off(pre_off, n + 1), h[n], h[n + 1]);
-      publish_u();
-      wait_acc();
-      if (warp * 32 < p.JD) {                    // warp-uniform: tcgen05.ld is .aligned
-        // h is dead: reuse it for the head outputs (lane = output feature j, column = row)
-        for_acc_cat<R, PRECISE>(taddr_cat, [&](int n, float v) { h[n] = v; });
+      for (int m = 0; m < 4; ++m) {
+        store_rows<PRECISE, 2>(h + m * NQ, stats_q, u_s, y0, y2, (uint32_t)(2 * m) * CBS, ok_tail, 0.f, 0.f);
+        publish_u(m);
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) wait_acc(m);
+      ++aphase;
+      // head epilogue with the lane = output feature view: warp group rq reads M-tile rq, all rows
+      if ((rq * 4 + lq) * 32 < p.JD) {           // warp-uniform: tcgen05.ld is .aligned
+        // h is dead: reuse it for the head outputs (lane = output feature, column = row)
+        for_acc_cat<R, PRECISE>(lane_base + (uint32_t)((rq % NACC) * ACC_COLS), [&](int n, float v) { h[n] = v; });
+        const int c = 128 * rq + c0;              // output feature
         if (c < p.JD && valid) {
           const float bo = p.w.b_out[c], sc = p.scale[b];
           const size_t base = ((size_t)b * p.JD + c) * LS_F;
@@ -674,8 +804,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           }
         }
       }
-      drained(p.MH);
-      // the next tile's X operand overwrites U: every head MMA has completed (wait_acc above)
+      // the next item's X operand overwrites U and its accumulators the head's: all reads above are done
       if (p.n_steps > 1) __threadfence();        // x_prev visible device-wide before the counter moves
       tc_fence_before_sync();
       epi_bar();
@@ -797,7 +926,7 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
     fs = new FusedState();
     fs->KIN = (h->JD + 63) / 64;
     fs->MH = (h->JD + 127) / 128;
-    if (fs->KIN > 8 || fs->MH > 4) {
+    if (fs->KIN > 8 || fs->MH > NACC) {      // the head's M-tiles each need their own accumulator buffer
       delete fs;
       return 1;
     }
@@ -910,8 +1039,8 @@ int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const l
     long long t[512];
     cudaStreamSynchronize(s);
     cudaMemcpy(t, tbuf, sizeof(t), cudaMemcpyDeviceToHost);
-    static const char* names[] = {"LN1 stats", "U1 publish", "tok acc wait", "tok epilogue", "U2 publish", "LN2 stats",
-                                  "ch acc wait", "ch epilogue"};
+    static const char* names[] = {"LN1 stats", "U1 publish", "tok epilogue + U2 publish", "LN2 stats", "ch acc 0 wait",
+                                  "ch epilogue m0-2", "ch epilogue m3"};
 #if LS_MMA_PROF
     fprintf(stderr, "[fused timing] MMA warp of CTA 0 over %lld rounds: total %lld cyc, waiting for weight stages %lld, "
                     "waiting for operand tiles %lld\n", t[511], t[510], t[508], t[509]);
@@ -919,9 +1048,9 @@ int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const l
     for (int w = 0; w < 2; ++w) {
       const long long* q = t + 256 * w;
       fprintf(stderr, "[fused timing] thread %d: X publish -> in-proj consumed %lld cyc\n", w ? 511 : 0, q[1] - q[0]);
-      for (int l = 0; l < h->cfg.n_layers && 2 + 8 * l + 7 < 256; ++l) {
+      for (int l = 0; l < h->cfg.n_layers && 2 + 7 * l + 6 < 256; ++l) {
         fprintf(stderr, "  layer %d:", l);
-        for (int k = 0; k < 8; ++k) fprintf(stderr, " %s %lld |", names[k], q[2 + 8 * l + k] - q[1 + 8 * l + k]);
+        for (int k = 0; k < 7; ++k) fprintf(stderr, " %s %lld |", names[k], q[2 + 7 * l + k] - q[1 + 7 * l + k]);
         fprintf(stderr, "\n");
       }
     }

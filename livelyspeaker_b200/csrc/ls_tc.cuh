@@ -171,6 +171,47 @@ __device__ __forceinline__ void tmem_ld8x2(uint32_t taddr_a, uint32_t taddr_b, f
   }
 }
 
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];\n\t"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"(taddr)
+               : "memory");
+  v[0] = __uint_as_float(r[0]);
+  v[1] = __uint_as_float(r[1]);
+}
+__device__ __forceinline__ void tmem_ld2x2(uint32_t taddr_a, uint32_t taddr_b, float* a, float* b) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%4];\n\t"
+               "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%2,%3}, [%5];\n\t"
+               "tcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr_a), "r"(taddr_b)
+               : "memory");
+  a[0] = __uint_as_float(r[0]);
+  a[1] = __uint_as_float(r[1]);
+  b[0] = __uint_as_float(r[2]);
+  b[1] = __uint_as_float(r[3]);
+}
+
+// 16 + 2 consecutive columns, one wait
+__device__ __forceinline__ void tmem_ld16p2(uint32_t taddr, float* a, float* b) {
+  uint32_t r[18];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%18];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x2.b32 {%16,%17}, [%19];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17])
+      : "r"(taddr), "r"(taddr + 16)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = __uint_as_float(r[i]);
+  b[0] = __uint_as_float(r[16]);
+  b[1] = __uint_as_float(r[17]);
+}
+
 // ---- descriptors -------------------------------------------------------------------------
 // Shared-memory matrix descriptor (64 bit):
 //   [0,14)  matrix start address >> 4          [16,30) leading-dim byte offset >> 4
