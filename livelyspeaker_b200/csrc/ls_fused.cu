@@ -78,12 +78,15 @@ constexpr int NSLOT = 4;
 #endif
 constexpr uint32_t W_HALF = 16384;              // 128 x 64 bf16 weight block (hi or lo) = one stage
 constexpr uint32_t WBLK_BLK = 10 * 1024;        // token-mix weights: 80 rows x 64 k = one stage
-// TMEM columns.  Channel-type GEMMs (input projection, channel mix, head) use 3 rotating buffers of
-// ACC_COLS: [0,72) W_hi*U_lo, [72,144) W_hi*U_hi + W_lo*U_hi, [144,152) overhang of the N=80 product.
-// Token-mix accumulators (N=80, one per M-tile) alias them; the two kinds are never live together.
+// TMEM columns.  Channel-type GEMMs (input projection, channel mix) alternate between two buffers of ACC_COLS:
+// [0,72) W_hi*U_lo, [72,144) W_hi*U_hi + W_lo*U_hi, [144,152) overhang of the N=80 product.  The token mix
+// alternates between two N=80 buffers behind them, so a channel mix may start while the last token-mix
+// accumulators are still being read.  The head (<= 3 M-tiles, read only when all are complete) uses three
+// ACC_COLS buffers from column 0.
 constexpr int ACC_COLS = 152;
-constexpr int NACC = 3;
+constexpr int NACC = 3;                         // head M-tiles at most
 constexpr int CAT_HI = 72;                      // first column of the hi-image product in a buffer
+constexpr int TOK_BASE = 2 * ACC_COLS;          // token-mix accumulators: TOK_BASE + (m & 1) * NROW
 constexpr int KMAX = LS_MAX_FUSED_STEPS;
 
 // shared memory map (offsets from a 1024-aligned base)
@@ -102,9 +105,9 @@ constexpr uint32_t OFF_TMEM = OFF_BARS + 24 * 8;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_DYN = SMEM_USED + 1024;         // + alignment slack
 static_assert(SMEM_DYN <= 232448, "shared memory budget");
-static_assert(NACC * ACC_COLS <= 512 && 4 * NROW <= 512, "TMEM budget");
+static_assert(NACC * ACC_COLS <= 512 && TOK_BASE + 2 * NROW <= 512, "TMEM budget");
 
-enum { BAR_FULL0 = 0, BAR_EMPTY0 = 4, BAR_UREADY0 = 8, BAR_ACC0 = 12, BAR_DRAIN = 16 };   // indices into the mbarrier array
+enum { BAR_FULL0 = 0, BAR_EMPTY0 = 4, BAR_UREADY0 = 8, BAR_ACC0 = 12, BAR_DRAIN0 = 16, BAR_TDRAIN0 = 18 };   // indices into the mbarrier array
 
 struct StepIO {
   const float* eps_c; const float* eps_u; const float* noise;
@@ -396,7 +399,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       mbar_init(&bars[BAR_UREADY0 + m], NT_EPI);  // every epilogue thread writes 18 rows of one channel of M-tile m
       mbar_init(&bars[BAR_ACC0 + m], 1);
     }
-    mbar_init(&bars[BAR_DRAIN], NT_EPI);          // accumulator buffer 0 has been read (M-tile 3 reuses it)
+    for (int i = 0; i < 2; ++i) {                 // accumulator buffer i has been read (M-tile i + 2 reuses it)
+      mbar_init(&bars[BAR_DRAIN0 + i], NT_EPI);
+      mbar_init(&bars[BAR_TDRAIN0 + i], NT_EPI);
+    }
     mbar_fence_init();
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
@@ -466,7 +472,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
    } else if (warp == 17) {
     // ================= MMA issuer ==========================================================
     {   // all 32 lanes run this role in lock step; one elected lane issues (see ls_tc.cuh)
-      uint32_t it = 0, uphase = 0, dphase = 0;
+      uint32_t it = 0, uphase = 0, dphase = 0, tphase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);    // provably warp-uniform copy
       constexpr uint32_t id_cat = idesc_bf16(128, NCAT, 0, 0), id_kk = idesc_bf16(128, NROW, 0, 0),
                          id_mk = idesc_bf16(128, NROW, 1, 0);
@@ -528,27 +534,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           release_stage();
         }
       };
-      // one full GEMM over all of U: n_mt M-tiles x n_kc 64-channel blocks
-      auto gemm_all = [&](int n_mt, int n_kc) {
-        wait_u_all();
+      // one full GEMM over all of U: n_mt M-tiles x n_kc 64-channel blocks.  by_k: the operand tile arrives
+      // M-tile by M-tile (channels 128 m .. 128 m + 127 = K blocks 2m, 2m+1), so the first M-tile starts on the
+      // K blocks that are already there while the epilogue warps are still storing the rest.
+      auto gemm_all = [&](int n_mt, int n_kc, bool by_k, bool head) {
+        if (!by_k) wait_u_all();
 #pragma unroll 1
         for (int mt = 0; mt < 4; ++mt) {
           if (mt < n_mt) {
-            if (mt == NACC) {         // buffer 0 again: M-tile 0's epilogue must have read it
-              mbar_wait_s(bars_s + 8 * BAR_DRAIN, dphase & 1);
-              ++dphase;
+            if (!head && mt >= 2) {   // buffer mt - 2 again: its epilogue must have read it
+              mbar_wait_s(bars_s + 8 * (BAR_DRAIN0 + mt - 2), dphase & 1);
               tc_fence_after_sync();
             }
+            const uint32_t d = tmem_u + (uint32_t)(head ? mt : (mt & 1)) * ACC_COLS;
 #pragma unroll 1
-            for (int kc = 0; kc < n_kc; ++kc)
-              gemm_pair(tmem_u + (uint32_t)(mt % NACC) * ACC_COLS, uk + (uint32_t)kc * BLK, kc == 0);
+            for (int kc = 0; kc < n_kc; ++kc) {
+              if (by_k && mt == 0 && (kc & 1) == 0) {
+                LS_PROF(prof_u, mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + (kc >> 1)), uphase & 1);)
+                tc_fence_after_sync();
+              }
+              gemm_pair(d, uk + (uint32_t)kc * BLK, kc == 0);
+            }
           }
           umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));    // M-tiles without work still flip their barrier
         }
+        if (by_k) ++uphase;
+        if (!head) ++dphase;
       };
 #pragma unroll 1
       for (int round = 0; round < n_rounds; ++round) {
-        gemm_all(4, KIN);                                  // input projection
+        gemm_all(4, KIN, false, false);                    // input projection
 #pragma unroll 1
         for (int l = 0; l < n_layers; ++l) {
           // token mix: D[mt][ch, row_out] = sum_row_in U^T[ch, row_in] * Wblk[row_out, row_in].
@@ -565,8 +580,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
 #pragma unroll 1
           for (uint32_t mt = 0; mt < 4; ++mt) {
             LS_PROF(prof_u, mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + mt), uphase & 1);)
+            if (mt >= 2) mbar_wait_s(bars_s + 8 * (BAR_TDRAIN0 + mt - 2), tphase & 1);   // token buffer mt - 2 read
             tc_fence_after_sync();
-            const uint32_t d = tmem_u + mt * NROW;
+            const uint32_t d = tmem_u + (uint32_t)TOK_BASE + (mt & 1) * NROW;
             const uint32_t ua = um + 2 * mt * BLK;         // lo image of this M-tile's channels, MN-major
 #pragma unroll
             for (uint32_t ks = 0; ks < 5; ++ks) {
@@ -580,11 +596,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
             umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));
           }
           ++uphase;
+          ++tphase;
 #pragma unroll
           for (int i = 0; i < NW; ++i) release_stage();
-          gemm_all(4, 8);                                  // channel mix
+          gemm_all(4, 8, true, false);                     // channel mix
         }
-        gemm_all(MH, 8);                                   // output head
+        gemm_all(MH, 8, true, true);                       // output head
       }
 #if LS_MMA_PROF
       if (p.timing != nullptr && blockIdx.x == 0 && lane == 0) {
@@ -627,9 +644,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       tc_fence_before_sync();
       mbar_arrive(&bars[BAR_UREADY0 + m]);
     };
-    auto drained = [&]() {          // this thread's part of accumulator buffer 0 is read (M-tile 3 reuses it)
+    auto drained = [&](int bar) {   // this thread's part of an accumulator buffer is read (M-tile m + 2 reuses it)
       tc_fence_before_sync();
-      mbar_arrive(&bars[BAR_DRAIN]);
+      mbar_arrive(&bars[bar]);
     };
     float h[72];                    // h[m * 18 + j]: channel c0 + 128 m, row r0 + j
     int tix = 0;
@@ -704,12 +721,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         wait_acc(m);
-        acc_rows<PRECISE>(lane_base + (uint32_t)((m % NACC) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
+        acc_rows<PRECISE>(lane_base + (uint32_t)((m & 1) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
                           [&](int j, float v) {
           const int n = r0 + j, tok = n >= S ? n - S : n;
           if (tok >= NPRE && n < R) h[m * NQ + j] += v;          // prefix-token rows keep their direct values
         });
-        if (m == 0) drained();
+        if (m < 2) drained(BAR_DRAIN0 + m);
       }
       ++aphase;
       stamp();   // 1: input projection consumed
@@ -739,9 +756,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           wait_acc(m);
-          acc_rows_tok(lane_base + (uint32_t)(m * NROW + r0), [&](int j, float v) {
+          acc_rows_tok(lane_base + (uint32_t)(TOK_BASE + (m & 1) * NROW + r0), [&](int j, float v) {
             if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[r0 + j]);
           });
+          if (m < 2) drained(BAR_TDRAIN0 + m);
           store_rows<PRECISE, 1>(h + m * NQ, stats_q, u_s, y0, y2, (uint32_t)(2 * m) * CBS, ok_tail, 0.f, 0.f);
           publish_u(m);
         }
@@ -760,12 +778,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           const float Sc = p.Sc[l * LS_D + c0 + 128 * m], tc = p.tc[l * LS_D + c0 + 128 * m];
           wait_acc(m);
           if (m == 0) stamp();   // first channel-mix accumulator ready
-          acc_rows<PRECISE>(lane_base + (uint32_t)((m % NACC) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
+          acc_rows<PRECISE>(lane_base + (uint32_t)((m & 1) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
                             [&](int j, float v) {
             const float2 r = gd_q[j];
             if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(fmaf(r.x, v, fmaf(r.y, Sc, tc)));
           });
-          if (m == 0) drained();
+          if (m < 2) drained(BAR_DRAIN0 + m);
           if (m == 2) stamp();   // three of four M-tiles consumed
         }
         ++aphase;
