@@ -68,7 +68,16 @@ constexpr uint32_t U_BYTES = 8 * CBS;
 constexpr uint32_t SLOT = 16384;                // ring slot = tape stage pitch
 constexpr int NSLOT = 4;
 #ifndef LS_MULTICAST
-#define LS_MULTICAST 1   // 1: weight stages fetched half by each CTA of the pair and multicast to both
+// 1: CTAs run as cluster pairs, every weight stage is fetched half by each CTA and multicast to both (half the
+//    L2 reads, but the pair advances in lock step through the shared ring).  0 (default): independent CTAs, every
+//    CTA streams the whole tape from L2 - measured 2 % faster at B = 512 (1255 vs 1229 steps/s): L2 delivers the
+//    5.9 TB/s without trouble and the shared-memory pipe, not L2, bounds the GEMM phases.
+#define LS_MULTICAST 0
+#endif
+#if LS_MULTICAST
+#define LS_CLUSTER_ATTR __cluster_dims__(2, 1, 1)
+#else
+#define LS_CLUSTER_ATTR
 #endif
 #ifndef LS_NOFETCH
 #define LS_NOFETCH 0     // diagnostic: 1 = the producer signals stages without copying (garbage results, pure MMA timing)
@@ -281,44 +290,68 @@ __device__ __forceinline__ uint32_t row_addr(uint32_t y0, uint32_t y2, int j) {
   const uint32_t x = (uint32_t)(((i & 1) << 4) | (((i >> 2) & 1) << 6));
   return (x ? (yb ^ x) : yb) + 128u * (uint32_t)((i & 1) + 4 * ((i >> 2) & 1)) + 128u * (uint32_t)(j - i);
 }
-//   MODE 0: (h - mean) * rstd * alpha + beta (LayerNorm 1)
+// Rows are stored in pairs with ONE 32-bit store per image instead of four 16-bit ones: lanes L and L^1 own
+// adjacent channels, the even lane takes row j of both channels and the odd lane row j+1 (one shuffle per pair).
+// y0p / y2p are the row_addr bases of the EVEN channel of the lane pair, moved to row 1 (resp. 3) for odd lanes.
+// The shared-memory pipe is the kernel's bottleneck (ncu: 16-bit stores of two lanes to the same word take two
+// wavefronts), so this quarters the store wavefronts and halves the instructions of the operand stores.
+template <bool PRECISE>
+__device__ __forceinline__ void store_pair(uint32_t addr, bool odd, float u0, float u1) {
+  const float recv = __shfl_xor_sync(0xffffffffu, odd ? u0 : u1, 1);
+  const float lo_ch = odd ? recv : u0, hi_ch = odd ? u1 : recv;      // channels c (even), c + 1 of this lane's row
+  const __nv_bfloat162 hi = __floats2bfloat162_rn(lo_ch, hi_ch);    // .x = lo_ch (low half = lower address)
+  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi);
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr + HI_OFF), "r"(hb));
+  if (PRECISE) {
+    const float r0 = lo_ch - __uint_as_float(hb << 16), r1 = hi_ch - __uint_as_float(hb & 0xFFFF0000u);
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(r0, r1);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&lo)));
+  }
+}
+
 //   MODE 1: (h - mean) * rstd               (provisional normalisation of the channel-mix operand)
 //   MODE 2: h                               (output head operand)
 template <bool PRECISE, int MODE>
-__device__ __forceinline__ void store_rows(const float* hm, const float2* st, uint32_t u_s, uint32_t y0, uint32_t y2,
-                                           uint32_t ch_off, bool ok_tail, float alpha, float beta) {
-  // Two row pairs per iteration with all shared LOADS ahead of the shared STORES: ptxas cannot prove that the
-  // statistics do not alias the operand tile, so a load placed after a store waits for it and the 20-instruction
-  // chains of consecutive pairs would run back to back instead of overlapping.
-  auto norm = [&](float v, float rstd, float nmr) {       // nmr = -mean * rstd
-    if (MODE == 2) return v;
-    const float u = fmaf(v, rstd, nmr);
-    return MODE == 0 ? fmaf(u, alpha, beta) : u;
-  };
+__device__ __forceinline__ void store_rows(const float* hm, const float2* st, uint32_t u_s, uint32_t y0p, uint32_t y2p,
+                                           uint32_t ch_off, bool odd, bool ok_tail) {
 #pragma unroll
-  for (int j = 0; j < NQ; j += 4) {
-    const bool two = (j + 2 < NQ);
-    float4 sa = make_float4(0.f, 1.f, 0.f, 1.f), sb = sa;
+  for (int j = 0; j < NQ; j += 2) {
+    float u0 = hm[j], u1 = hm[j + 1];
     if (MODE != 2) {
-      sa = *reinterpret_cast<const float4*>(st + j);                 // (rstd, -mean*rstd) of rows j, j+1
-      if (two) sb = *reinterpret_cast<const float4*>(st + j + 2);
+      const float4 s4 = *reinterpret_cast<const float4*>(st + j);      // (rstd, -mean*rstd) of rows j, j+1
+      u0 = fmaf(u0, s4.x, s4.y);
+      u1 = fmaf(u1, s4.z, s4.w);
     }
-    const float a0 = norm(hm[j], sa.x, sa.y), a1 = norm(hm[j + 1], sa.z, sa.w);
-    float b0 = 0.f, b1 = 0.f;
-    if (two) {
-      b0 = norm(hm[j + 2], sb.x, sb.y);
-      b1 = norm(hm[j + 3], sb.z, sb.w);
+    // the shuffle inside is executed by every lane; only the stores of the missing tail rows are skipped
+    if (j < 16 || ok_tail) store_pair<PRECISE>(u_s + row_addr(y0p, y2p, j) + ch_off, odd, u0, u1);
+  }
+}
+
+// LayerNorm 1: (h - mean) * rstd * alpha + beta for channels M0, M0 + 1 of the thread; the statistics of a row
+// pair are loaded once for both.  (Two channels per call: M-tiles 0-1 are published - and their token mix
+// starts - while M-tiles 2-3 are still being stored.)
+template <bool PRECISE, int M0>
+__device__ __forceinline__ void store_rows_ln1(const float (&h)[72], const float2* st, float2 ab0, float2 ab1, uint32_t u_s,
+                                               uint32_t y0p, uint32_t y2p, bool odd, bool ok_tail) {
+#pragma unroll
+  for (int j = 0; j < NQ; j += 2) {
+    const float4 s4 = *reinterpret_cast<const float4*>(st + j);
+    if (j < 16 || ok_tail) {
+#pragma unroll
+      for (int m = M0; m < M0 + 2; ++m) {
+        const float2 ab = (m == M0) ? ab0 : ab1;
+        const float u0 = fmaf(fmaf(h[m * NQ + j], s4.x, s4.y), ab.x, ab.y);
+        const float u1 = fmaf(fmaf(h[m * NQ + j + 1], s4.z, s4.w), ab.x, ab.y);
+        store_pair<PRECISE>(u_s + row_addr(y0p, y2p, j) + (uint32_t)(2 * m) * CBS, odd, u0, u1);
+      }
     }
-    if (j < 16 || ok_tail) store_split2<PRECISE>(u_s, row_addr(y0, y2, j) + ch_off, row_addr(y0, y2, j + 1) + ch_off, a0, a1);
-    if (two && (j + 2 < 16 || ok_tail))
-      store_split2<PRECISE>(u_s, row_addr(y0, y2, j + 2) + ch_off, row_addr(y0, y2, j + 3) + ch_off, b0, b1);
   }
 }
 
 // This thread's 18 columns [taddr, taddr + 18) of one accumulator (CAT: plus the columns 72 further that hold
 // the other partial product) handed to f(j, value) with compile-time j.  Whole warps only.
 template <bool CAT, class F>
-__device__ __forceinline__ void acc_rows(uint32_t taddr, F&& f) {
+__device__ __forceinline__ void acc_rows(uint32_t taddr, F&& f) {     // f(j, v_j, v_j+1), j even
 #pragma unroll
   for (int c0 = 0; c0 < 16; c0 += 8) {
     float a[8], b[8];
@@ -330,13 +363,12 @@ __device__ __forceinline__ void acc_rows(uint32_t taddr, F&& f) {
       for (int i = 0; i < 8; ++i) b[i] = 0.f;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) f(c0 + i, a[i] + b[i]);
+    for (int i = 0; i < 8; i += 2) f(c0 + i, a[i] + b[i], a[i + 1] + b[i + 1]);
   }
   float a[2], b[2] = {0.f, 0.f};
   if (CAT) tmem_ld2x2(taddr + 16, taddr + CAT_HI + 16, a, b);
   else tmem_ld2(taddr + 16, a);
-  f(16, a[0] + b[0]);
-  f(17, a[1] + b[1]);
+  f(16, a[0] + b[0], a[1] + b[1]);
 }
 
 // Token-mix accumulator: the 18 columns in ONE load round (16 + 2, a single wait).
@@ -376,7 +408,7 @@ template <int S>
 struct TokBias { static constexpr bool kInGemm = (2 * S + 1 <= 72); };
 
 template <int S, bool PRECISE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
+__global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(const __grid_constant__ FusedParams p) {
   constexpr int R = 2 * S;            // real rows of a tile
   constexpr int NPRE = S - LS_F;      // prefix tokens per pass
   static_assert(R <= 72, "tile rows");
@@ -411,15 +443,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
     sts_u16(smem_u32(sm + OFF_U) + HI_OFF + tile_off(R, tid, CBS), (uint16_t)0x3F80u);
   fence_proxy_async_smem();
   tc_fence_before_sync();
+#if LS_MULTICAST
   cluster_sync_all();             // barriers of both CTAs initialised before any multicast touches them
+#else
+  __syncthreads();
+#endif
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // The two CTAs of a cluster consume ONE weight stream (every stage is fetched half by each CTA and
-  // multicast to both), so they run the same number of rounds; a CTA without a real item in the
-  // last round recomputes item 0 and writes nothing.
+  // Every CTA runs the same number of rounds (with LS_MULTICAST the two CTAs of a cluster consume ONE weight
+  // stream and must); a CTA without a real item in the last round recomputes item 0 and writes nothing.
   const int n_items = p.B * p.n_steps;
   const int n_rounds = (n_items + (int)gridDim.x - 1) / (int)gridDim.x;
+#if LS_MULTICAST
   const uint32_t cta_rank = cluster_ctarank();
+#endif
 
   if (warp >= 16) {
    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_AUX));
@@ -627,11 +664,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
     const float2* stats_q = reinterpret_cast<const float2*>(sm + OFF_STATS) + r0;
     const float2* gd_q = reinterpret_cast<const float2*>(sm + OFF_GD) + r0;
     const uint32_t u_s = smem_u32(sm + OFF_U);
-    uint32_t y0, y2;                              // see row_addr
+    const bool odd = (lane & 1) != 0;
+    uint32_t y0p, y2p;                            // see row_addr / store_pair
     {
-      const uint32_t pre = (uint32_t)(c0 >> 6) * CBS + (uint32_t)(((c0 & 63) >> 3) << 4) + (uint32_t)(c0 & 7) * 2u;
-      y0 = (pre ^ ((uint32_t)((2 * rq) & 7) << 4)) + 128u * (uint32_t)r0;
-      y2 = (pre ^ ((uint32_t)((2 * rq + 2) & 7) << 4)) + 128u * (uint32_t)(r0 + 2);
+      const int ce = c0 & ~1;                     // even channel of the lane pair
+      const uint32_t pre = (uint32_t)(ce >> 6) * CBS + (uint32_t)(((ce & 63) >> 3) << 4) + (uint32_t)(ce & 7) * 2u;
+      y0p = (pre ^ ((uint32_t)((2 * rq) & 7) << 4)) + 128u * (uint32_t)r0;
+      y2p = (pre ^ ((uint32_t)((2 * rq + 2) & 7) << 4)) + 128u * (uint32_t)(r0 + 2);
+      if (odd) {                                  // odd lanes store row j + 1 of the pair
+        y0p = (y0p ^ 16u) + 128u;
+        y2p = (y2p ^ 16u) + 128u;
+      }
     }
     uint32_t aphase = 0;
     auto wait_acc = [&](int m) {
@@ -722,9 +765,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       for (int m = 0; m < 4; ++m) {
         wait_acc(m);
         acc_rows<PRECISE>(lane_base + (uint32_t)((m & 1) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
-                          [&](int j, float v) {
-          const int n = r0 + j, tok = n >= S ? n - S : n;
-          if (tok >= NPRE && n < R) h[m * NQ + j] += v;          // prefix-token rows keep their direct values
+                          [&](int j, float v0, float v1) {
+          const int n = r0 + j, tok = n >= S ? n - S : n, n1 = n + 1, tok1 = n1 >= S ? n1 - S : n1;
+          if (tok >= NPRE && n < R) h[m * NQ + j] += v0;         // prefix-token rows keep their direct values
+          if (tok1 >= NPRE && n1 < R) h[m * NQ + j + 1] += v1;
         });
         if (m < 2) drained(BAR_DRAIN0 + m);
       }
@@ -744,12 +788,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
         if (l == 0) ln_stats_q<0>(h, sm, rq, false);     // provisional means for the shift
         ln_stats_q<0>(h, sm, rq, true);
         stamp();   // LN1 stats done
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const float2 ab = pab_s[c0 + 128 * m];
-          store_rows<PRECISE, 0>(h + m * NQ, stats_q, u_s, y0, y2, (uint32_t)(2 * m) * CBS, ok_tail, ab.x, ab.y);
-          publish_u(m);
-        }
+        store_rows_ln1<PRECISE, 0>(h, stats_q, pab_s[c0], pab_s[c0 + 128], u_s, y0p, y2p, odd, ok_tail);
+        publish_u(0);
+        publish_u(1);
+        store_rows_ln1<PRECISE, 2>(h, stats_q, pab_s[c0 + 256], pab_s[c0 + 384], u_s, y0p, y2p, odd, ok_tail);
+        publish_u(2);
+        publish_u(3);
         stamp();   // U1 published
         // token mix epilogue x = x + silu(conv + bias), then straight into the channel-mix operand:
         // normalised with the LN1 statistics; the exact LN2 statistics follow while the GEMM runs
@@ -760,7 +804,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
             if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[r0 + j]);
           });
           if (m < 2) drained(BAR_TDRAIN0 + m);
-          store_rows<PRECISE, 1>(h + m * NQ, stats_q, u_s, y0, y2, (uint32_t)(2 * m) * CBS, ok_tail, 0.f, 0.f);
+          store_rows<PRECISE, 1>(h + m * NQ, stats_q, u_s, y0p, y2p, (uint32_t)(2 * m) * CBS, odd, ok_tail);
           publish_u(m);
         }
         ++aphase;
@@ -779,9 +823,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
           wait_acc(m);
           if (m == 0) stamp();   // first channel-mix accumulator ready
           acc_rows<PRECISE>(lane_base + (uint32_t)((m & 1) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
-                            [&](int j, float v) {
-            const float2 r = gd_q[j];
-            if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(fmaf(r.x, v, fmaf(r.y, Sc, tc)));
+                            [&](int j, float v0, float v1) {
+            const float4 r = *reinterpret_cast<const float4*>(gd_q + j);     // (scale, shift) of rows j, j+1
+            if (j < 16 || ok_tail) {
+              h[m * NQ + j] += silu_fast(fmaf(r.x, v0, fmaf(r.y, Sc, tc)));
+              h[m * NQ + j + 1] += silu_fast(fmaf(r.z, v1, fmaf(r.w, Sc, tc)));
+            }
           });
           if (m < 2) drained(BAR_DRAIN0 + m);
           if (m == 2) stamp();   // three of four M-tiles consumed
@@ -794,7 +841,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
       // This thread has waited for every M-tile of the last channel mix, so all MMAs reading U are complete.
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        store_rows<PRECISE, 2>(h + m * NQ, stats_q, u_s, y0, y2, (uint32_t)(2 * m) * CBS, ok_tail, 0.f, 0.f);
+        store_rows<PRECISE, 2>(h + m * NQ, stats_q, u_s, y0p, y2p, (uint32_t)(2 * m) * CBS, odd, ok_tail);
         publish_u(m);
       }
 #pragma unroll
@@ -831,7 +878,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NT_ALL, 1) fused_ste
   }
   // ---- teardown ---------------------------------------------------------------------------
   tc_fence_before_sync();
+#if LS_MULTICAST
   cluster_sync_all();             // the peer may still multicast commits into this CTA's barriers
+#else
+  __syncthreads();
+#endif
   if (warp == 17) tmem_dealloc<512>(tmem);
 }
 
@@ -911,9 +962,13 @@ int launch_fused(ls_handle* h, FusedState* fs, const FusedParams& fp, cudaStream
     LS_CUDA(h, cudaFuncSetAttribute(fused_step_kernel<S, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN));
     done = true;
   }
-  // clusters of 2: an even grid, at most one CTA per SM
+  // at most one CTA per SM (all CTAs co-resident: the step counters rely on it); cluster pairs need an even grid
   const int items = fp.B * fp.n_steps;
+#if LS_MULTICAST
   const int grid = (items + 1 < fs->sm_count ? items + 1 : fs->sm_count) & ~1;
+#else
+  const int grid = items < fs->sm_count ? items : fs->sm_count;
+#endif
   fused_step_kernel<S, PRECISE><<<grid, NT_ALL, SMEM_DYN, s>>>(fp);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
@@ -1013,7 +1068,7 @@ int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const l
   FusedState* fs = static_cast<FusedState*>(h->fused);
   if (!fs) return ls_fail(h, LS_EUNSUPPORTED, "tcgen05 path not available");
   if (n_steps < 1 || n_steps > KMAX) return ls_fail(h, LS_EINVAL, "n_steps %d outside [1,%d]", n_steps, KMAX);
-  if (n_steps > 1 && B < 2) {
+  if (LS_MULTICAST && n_steps > 1 && B < 2) {
     // With one clip the two CTAs of a cluster would hold consecutive steps of the SAME clip: the second waits
     // for the first, which in turn needs its peer to drain the shared weight ring.  Run step by step.
     for (int k = 0; k < n_steps; ++k) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Diagnostic builds of libls_b200.so (selected at run time with LS_B200_LIB=<path>):
 #   libls_prof.so     MMA-warp cycle accounting (LS_FUSED_TIMING=1 prints it)
-#   libls_nomc.so     no cluster multicast: every CTA streams the whole weight tape from L2
+#   libls_mc.so       cluster pairs with multicast weight stages (half the L2 reads, pair in lock step)
 #   libls_nofetch.so  the producer signals stages without copying: pure MMA / epilogue timing, garbage results
 set -e
 cd "$(dirname "$0")/../livelyspeaker_b200/csrc"
@@ -14,7 +14,7 @@ build() {  # name, extra flags
   $NVCC $ARCH -shared -o libls_$1.so ls_api.o ls_precompute.o ls_denoise_simt.o ls_update.o /tmp/ls_fused_$1.o
 }
 build prof "-DLS_MMA_PROF=1" &
-build nomc "-DLS_MULTICAST=0 -DLS_MMA_PROF=1" &
+build mc "-DLS_MULTICAST=1 -DLS_MMA_PROF=1" &
 build nofetch "-DLS_NOFETCH=1 -DLS_MMA_PROF=1" &
 wait
 ls -la libls_*.so
