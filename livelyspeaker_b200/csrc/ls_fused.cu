@@ -291,10 +291,12 @@ __device__ __forceinline__ uint32_t row_addr(uint32_t y0, uint32_t y2, int j) {
   return (x ? (yb ^ x) : yb) + 128u * (uint32_t)((i & 1) + 4 * ((i >> 2) & 1)) + 128u * (uint32_t)(j - i);
 }
 // Rows are stored in pairs with ONE 32-bit store per image instead of four 16-bit ones: lanes L and L^1 own
-// adjacent channels, the even lane takes row j of both channels and the odd lane row j+1 (one shuffle per pair).
-// y0p / y2p are the row_addr bases of the EVEN channel of the lane pair, moved to row 1 (resp. 3) for odd lanes.
-// The shared-memory pipe is the kernel's bottleneck (ncu: 16-bit stores of two lanes to the same word take two
-// wavefronts), so this quarters the store wavefronts and halves the instructions of the operand stores.
+// adjacent channels; of a row pair (j, j+4) the even lane stores row j of both channels and the odd lane row j+4
+// (one shuffle per pair).  Rows j and j+4 differ in bit 2 of the swizzle, so the two half-warps hit disjoint halves
+// of the 32 banks: one wavefront per store.  (Pairing rows j, j+1 would put both halves on the same 16 banks, and
+// two lanes writing the 16-bit halves of one word take two wavefronts as well - measured with ncu; the shared-
+// memory pipe is this kernel's bottleneck.)  ya0 / ya2: row_addr bases of the EVEN channel of the lane pair for
+// rows 0 / 2 of the thread, moved 4 rows down for odd lanes; ytail: address of row 16 (even) / 17 (odd lanes).
 template <bool PRECISE>
 __device__ __forceinline__ void store_pair(uint32_t addr, bool odd, float u0, float u1) {
   const float recv = __shfl_xor_sync(0xffffffffu, odd ? u0 : u1, 1);
@@ -309,41 +311,61 @@ __device__ __forceinline__ void store_pair(uint32_t addr, bool odd, float u0, fl
   }
 }
 
+struct RowBases { uint32_t ya0, ya2, ytail; };
+
 //   MODE 1: (h - mean) * rstd               (provisional normalisation of the channel-mix operand)
 //   MODE 2: h                               (output head operand)
 template <bool PRECISE, int MODE>
-__device__ __forceinline__ void store_rows(const float* hm, const float2* st, uint32_t u_s, uint32_t y0p, uint32_t y2p,
+__device__ __forceinline__ void store_rows(const float* hm, const float2* st, uint32_t u_s, const RowBases& rb,
                                            uint32_t ch_off, bool odd, bool ok_tail) {
+  auto norm = [&](float v, float rstd, float nmr) { return MODE == 2 ? v : fmaf(v, rstd, nmr); };
 #pragma unroll
-  for (int j = 0; j < NQ; j += 2) {
-    float u0 = hm[j], u1 = hm[j + 1];
+  for (int j = 0; j < 16; j += 2) {
+    if ((j & 4) != 0) continue;              // j = 0, 2, 8, 10: row pairs (j, j+4) and (j+1, j+5)
+    float4 sa = make_float4(1.f, 0.f, 1.f, 0.f), sb = sa;
     if (MODE != 2) {
-      const float4 s4 = *reinterpret_cast<const float4*>(st + j);      // (rstd, -mean*rstd) of rows j, j+1
-      u0 = fmaf(u0, s4.x, s4.y);
-      u1 = fmaf(u1, s4.z, s4.w);
+      sa = *reinterpret_cast<const float4*>(st + j);          // (rstd, -mean*rstd) of rows j, j+1
+      sb = *reinterpret_cast<const float4*>(st + j + 4);      // ... of rows j+4, j+5
     }
-    // the shuffle inside is executed by every lane; only the stores of the missing tail rows are skipped
-    if (j < 16 || ok_tail) store_pair<PRECISE>(u_s + row_addr(y0p, y2p, j) + ch_off, odd, u0, u1);
+    store_pair<PRECISE>(u_s + row_addr(rb.ya0, rb.ya2, j) + ch_off, odd, norm(hm[j], sa.x, sa.y), norm(hm[j + 4], sb.x, sb.y));
+    store_pair<PRECISE>(u_s + row_addr(rb.ya0, rb.ya2, j + 1) + ch_off, odd, norm(hm[j + 1], sa.z, sa.w),
+                        norm(hm[j + 5], sb.z, sb.w));
+  }
+  if (ok_tail) {                             // warp-uniform; rows 16, 17
+    float4 sa = make_float4(1.f, 0.f, 1.f, 0.f);
+    if (MODE != 2) sa = *reinterpret_cast<const float4*>(st + 16);
+    store_pair<PRECISE>(u_s + rb.ytail + ch_off, odd, norm(hm[16], sa.x, sa.y), norm(hm[17], sa.z, sa.w));
   }
 }
 
 // LayerNorm 1: (h - mean) * rstd * alpha + beta for channels M0, M0 + 1 of the thread; the statistics of a row
-// pair are loaded once for both.  (Two channels per call: M-tiles 0-1 are published - and their token mix
-// starts - while M-tiles 2-3 are still being stored.)
+// are loaded once for both.  (Two channels per call: M-tiles 0-1 are published - and their token mix starts -
+// while M-tiles 2-3 are still being stored.)
 template <bool PRECISE, int M0>
 __device__ __forceinline__ void store_rows_ln1(const float (&h)[72], const float2* st, float2 ab0, float2 ab1, uint32_t u_s,
-                                               uint32_t y0p, uint32_t y2p, bool odd, bool ok_tail) {
+                                               const RowBases& rb, bool odd, bool ok_tail) {
 #pragma unroll
-  for (int j = 0; j < NQ; j += 2) {
-    const float4 s4 = *reinterpret_cast<const float4*>(st + j);
-    if (j < 16 || ok_tail) {
+  for (int j = 0; j < 16; j += 2) {
+    if ((j & 4) != 0) continue;
+    const float4 sa = *reinterpret_cast<const float4*>(st + j), sb = *reinterpret_cast<const float4*>(st + j + 4);
 #pragma unroll
-      for (int m = M0; m < M0 + 2; ++m) {
-        const float2 ab = (m == M0) ? ab0 : ab1;
-        const float u0 = fmaf(fmaf(h[m * NQ + j], s4.x, s4.y), ab.x, ab.y);
-        const float u1 = fmaf(fmaf(h[m * NQ + j + 1], s4.z, s4.w), ab.x, ab.y);
-        store_pair<PRECISE>(u_s + row_addr(y0p, y2p, j) + (uint32_t)(2 * m) * CBS, odd, u0, u1);
-      }
+    for (int m = M0; m < M0 + 2; ++m) {
+      const float2 ab = (m == M0) ? ab0 : ab1;
+      const float* hm = h + m * NQ;
+      const uint32_t base = u_s + (uint32_t)(2 * m) * CBS;
+      store_pair<PRECISE>(base + row_addr(rb.ya0, rb.ya2, j), odd, fmaf(fmaf(hm[j], sa.x, sa.y), ab.x, ab.y),
+                          fmaf(fmaf(hm[j + 4], sb.x, sb.y), ab.x, ab.y));
+      store_pair<PRECISE>(base + row_addr(rb.ya0, rb.ya2, j + 1), odd, fmaf(fmaf(hm[j + 1], sa.z, sa.w), ab.x, ab.y),
+                          fmaf(fmaf(hm[j + 5], sb.z, sb.w), ab.x, ab.y));
+    }
+  }
+  if (ok_tail) {
+    const float4 sa = *reinterpret_cast<const float4*>(st + 16);
+#pragma unroll
+    for (int m = M0; m < M0 + 2; ++m) {
+      const float2 ab = (m == M0) ? ab0 : ab1;
+      store_pair<PRECISE>(u_s + (uint32_t)(2 * m) * CBS + rb.ytail, odd, fmaf(fmaf(h[m * NQ + 16], sa.x, sa.y), ab.x, ab.y),
+                          fmaf(fmaf(h[m * NQ + 17], sa.z, sa.w), ab.x, ab.y));
     }
   }
 }
@@ -428,12 +450,12 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
       mbar_init(&bars[BAR_EMPTY0 + s], LS_MULTICAST ? 2 : 1);   // multicast: the MMA issuers of BOTH CTAs release a slot
     }
     for (int m = 0; m < 4; ++m) {
-      mbar_init(&bars[BAR_UREADY0 + m], NT_EPI);  // every epilogue thread writes 18 rows of one channel of M-tile m
+      mbar_init(&bars[BAR_UREADY0 + m], NT_EPI / 32);  // one arrival per epilogue warp (every thread writes a part of M-tile m)
       mbar_init(&bars[BAR_ACC0 + m], 1);
     }
     for (int i = 0; i < 2; ++i) {                 // accumulator buffer i has been read (M-tile i + 2 reuses it)
-      mbar_init(&bars[BAR_DRAIN0 + i], NT_EPI);
-      mbar_init(&bars[BAR_TDRAIN0 + i], NT_EPI);
+      mbar_init(&bars[BAR_DRAIN0 + i], NT_EPI / 32);
+      mbar_init(&bars[BAR_TDRAIN0 + i], NT_EPI / 32);
     }
     mbar_fence_init();
   }
@@ -665,16 +687,15 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
     const float2* gd_q = reinterpret_cast<const float2*>(sm + OFF_GD) + r0;
     const uint32_t u_s = smem_u32(sm + OFF_U);
     const bool odd = (lane & 1) != 0;
-    uint32_t y0p, y2p;                            // see row_addr / store_pair
+    RowBases rb;                                  // see row_addr / store_pair
     {
       const int ce = c0 & ~1;                     // even channel of the lane pair
       const uint32_t pre = (uint32_t)(ce >> 6) * CBS + (uint32_t)(((ce & 63) >> 3) << 4) + (uint32_t)(ce & 7) * 2u;
-      y0p = (pre ^ ((uint32_t)((2 * rq) & 7) << 4)) + 128u * (uint32_t)r0;
-      y2p = (pre ^ ((uint32_t)((2 * rq + 2) & 7) << 4)) + 128u * (uint32_t)(r0 + 2);
-      if (odd) {                                  // odd lanes store row j + 1 of the pair
-        y0p = (y0p ^ 16u) + 128u;
-        y2p = (y2p ^ 16u) + 128u;
-      }
+      const uint32_t y0 = (pre ^ ((uint32_t)((2 * rq) & 7) << 4)) + 128u * (uint32_t)r0;
+      const uint32_t y2 = (pre ^ ((uint32_t)((2 * rq + 2) & 7) << 4)) + 128u * (uint32_t)(r0 + 2);
+      rb.ya0 = odd ? (y0 ^ 64u) + 512u : y0;      // odd lanes store row j + 4 of a pair (j, j+4)
+      rb.ya2 = odd ? (y2 ^ 64u) + 512u : y2;
+      rb.ytail = (odd ? (y0 ^ 16u) + 128u : y0) + 128u * 16u;     // rows 16 / 17
     }
     uint32_t aphase = 0;
     auto wait_acc = [&](int m) {
@@ -682,14 +703,19 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
       __syncwarp();                 // the spin loop may leave the warp diverged; tcgen05.ld is .aligned
       tc_fence_after_sync();
     };
-    auto publish_u = [&](int m) {   // this thread's part of the operand channels of M-tile m is written
+    // One mbarrier arrival per WARP: 32 lanes arriving on the same barrier are 32 serialised shared-memory
+    // atomics (ncu: a fifth of all shared wavefronts).  Each lane fences its own writes / TMEM reads, the warp
+    // syncs, lane 0 arrives.
+    auto publish_u = [&](int m) {   // this warp's part of the operand channels of M-tile m is written
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&bars[BAR_UREADY0 + m]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_UREADY0 + m]);
     };
-    auto drained = [&](int bar) {   // this thread's part of an accumulator buffer is read (M-tile m + 2 reuses it)
+    auto drained = [&](int bar) {   // this warp's part of an accumulator buffer is read (M-tile m + 2 reuses it)
       tc_fence_before_sync();
-      mbar_arrive(&bars[bar]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[bar]);
     };
     float h[72];                    // h[m * 18 + j]: channel c0 + 128 m, row r0 + j
     int tix = 0;
@@ -788,10 +814,10 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         if (l == 0) ln_stats_q<0>(h, sm, rq, false);     // provisional means for the shift
         ln_stats_q<0>(h, sm, rq, true);
         stamp();   // LN1 stats done
-        store_rows_ln1<PRECISE, 0>(h, stats_q, pab_s[c0], pab_s[c0 + 128], u_s, y0p, y2p, odd, ok_tail);
+        store_rows_ln1<PRECISE, 0>(h, stats_q, pab_s[c0], pab_s[c0 + 128], u_s, rb, odd, ok_tail);
         publish_u(0);
         publish_u(1);
-        store_rows_ln1<PRECISE, 2>(h, stats_q, pab_s[c0 + 256], pab_s[c0 + 384], u_s, y0p, y2p, odd, ok_tail);
+        store_rows_ln1<PRECISE, 2>(h, stats_q, pab_s[c0 + 256], pab_s[c0 + 384], u_s, rb, odd, ok_tail);
         publish_u(2);
         publish_u(3);
         stamp();   // U1 published
@@ -804,7 +830,7 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
             if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[r0 + j]);
           });
           if (m < 2) drained(BAR_TDRAIN0 + m);
-          store_rows<PRECISE, 1>(h + m * NQ, stats_q, u_s, y0p, y2p, (uint32_t)(2 * m) * CBS, odd, ok_tail);
+          store_rows<PRECISE, 1>(h + m * NQ, stats_q, u_s, rb, (uint32_t)(2 * m) * CBS, odd, ok_tail);
           publish_u(m);
         }
         ++aphase;
@@ -841,7 +867,7 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
       // This thread has waited for every M-tile of the last channel mix, so all MMAs reading U are complete.
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        store_rows<PRECISE, 2>(h + m * NQ, stats_q, u_s, y0p, y2p, (uint32_t)(2 * m) * CBS, odd, ok_tail);
+        store_rows<PRECISE, 2>(h + m * NQ, stats_q, u_s, rb, (uint32_t)(2 * m) * CBS, odd, ok_tail);
         publish_u(m);
       }
 #pragma unroll
