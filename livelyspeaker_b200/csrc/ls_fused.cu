@@ -108,7 +108,8 @@ constexpr uint32_t OFF_MEAN = OFF_STATS + 72 * 8;       // [72] float mean (the 
 constexpr uint32_t OFF_GD = OFF_MEAN + 72 * 4;          // [72] float2 channel-mix epilogue (row scale, row shift)
 constexpr uint32_t OFF_BTOK = OFF_GD + 72 * 8;          // [72] float token-mix bias
 constexpr uint32_t OFF_PAB = OFF_BTOK + 72 * 4;         // [512] float2 (ln1 alpha, beta) of the current layer, thread-private slots
-constexpr uint32_t OFF_EMB = OFF_PAB + 512 * 8;         // [512] float time embedding of the current item, thread-private slots
+constexpr uint32_t OFF_PSC = OFF_PAB + 512 * 8;         // [512] float2 (S_c, t_c) of the current layer, thread-private slots
+constexpr uint32_t OFF_EMB = OFF_PSC + 512 * 8;         // [512] float time embedding of the current item, thread-private slots
 constexpr uint32_t OFF_BARS = OFF_EMB + 512 * 4;         // mbarriers
 constexpr uint32_t OFF_TMEM = OFF_BARS + 24 * 8;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
@@ -683,6 +684,7 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
     float* btok_s = reinterpret_cast<float*>(sm + OFF_BTOK);
     float* emb_s = reinterpret_cast<float*>(sm + OFF_EMB);
     float2* pab_s = reinterpret_cast<float2*>(sm + OFF_PAB);
+    float2* psc_s = reinterpret_cast<float2*>(sm + OFF_PSC);
     const float2* stats_q = reinterpret_cast<const float2*>(sm + OFF_STATS) + r0;
     const float2* gd_q = reinterpret_cast<const float2*>(sm + OFF_GD) + r0;
     const uint32_t u_s = smem_u32(sm + OFF_U);
@@ -836,17 +838,28 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         ++aphase;
         stamp();   // token-mix epilogue done, U2 published
         ln_stats_q<1>(h, sm, rq, true);
-        if (l + 1 < p.n_layers) {     // next layer's LayerNorm-1 parameters; the L2 latency disappears in the wait below
-          const LsLayerW& Ln = p.w.layer[l + 1];
+        {     // this layer's channel-mix fold terms and the next layer's LayerNorm-1 parameters: one L2 round trip here,
+              // next to the accumulator wait, instead of one per M-tile inside the epilogue (10 % of the stall samples)
+          float2 sc[4], ab[4];
+          const LsLayerW& Ln = p.w.layer[l + 1 < p.n_layers ? l + 1 : l];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) pab_s[c0 + 128 * m] = make_float2(Ln.ln1_a[c0 + 128 * m], Ln.ln1_b[c0 + 128 * m]);
+          for (int m = 0; m < 4; ++m) {
+            sc[m] = make_float2(p.Sc[l * LS_D + c0 + 128 * m], p.tc[l * LS_D + c0 + 128 * m]);
+            ab[m] = make_float2(Ln.ln1_a[c0 + 128 * m], Ln.ln1_b[c0 + 128 * m]);
+          }
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            psc_s[c0 + 128 * m] = sc[m];
+            pab_s[c0 + 128 * m] = ab[m];
+          }
         }
         stamp();   // LN2 stats done (under the GEMM)
         // channel mix epilogue: x = x + silu(linear + bias)
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const float Sc = p.Sc[l * LS_D + c0 + 128 * m], tc = p.tc[l * LS_D + c0 + 128 * m];
           wait_acc(m);
+          const float2 sct = psc_s[c0 + 128 * m];
+          const float Sc = sct.x, tc = sct.y;
           if (m == 0) stamp();   // first channel-mix accumulator ready
           acc_rows<PRECISE>(lane_base + (uint32_t)((m & 1) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
                             [&](int j, float v0, float v1) {
@@ -883,15 +896,29 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
           const size_t base = ((size_t)b * p.JD + c) * LS_F;
           const float* nzp = io.noise ? io.noise + (size_t)b * io.nsb + (size_t)c * io.nsj : nullptr;
           const bool use_noise = (sp.mode != 2) && sp.add_noise && nzp != nullptr;
+          // guidance first (frees the uncond half), then the sampler update in two batches whose global LOADS are
+          // all issued before the first STORE: x_prev may alias x_t, so the compiler cannot hoist a load above a
+          // store and a load-per-frame loop would pay one L2 round trip per frame on a single warp.
 #pragma unroll
           for (int f = 0; f < LS_F; ++f) {
             const float oc = h[NPRE + f] + bo, ou = h[S + NPRE + f] + bo;
-            float x0 = ou + sc * (oc - ou);                       // cfg_sampler.py:31
-            const float nz = use_noise ? nzp[(size_t)f * io.nsf] : 0.f;
-            float xp = 0.f;
-            x0 = ls_sampler_update(sp, x0, __ldcg(x_t + base + f), nz, &xp);
-            if (io.pred_x0) io.pred_x0[base + f] = x0;
-            if (sp.mode != 2) io.x_prev[base + f] = xp;
+            h[NPRE + f] = ou + sc * (oc - ou);                    // cfg_sampler.py:31
+          }
+#pragma unroll
+          for (int f0 = 0; f0 < LS_F; f0 += 17) {
+            float xt[17], nz[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+              xt[i] = __ldcg(x_t + base + f0 + i);
+              nz[i] = use_noise ? nzp[(size_t)(f0 + i) * io.nsf] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 17; ++i) {
+              float xp = 0.f;
+              const float x0 = ls_sampler_update(sp, h[NPRE + f0 + i], xt[i], nz[i], &xp);
+              if (io.pred_x0) io.pred_x0[base + f0 + i] = x0;
+              if (sp.mode != 2) io.x_prev[base + f0 + i] = xp;
+            }
           }
         }
       }

@@ -1,0 +1,40 @@
+"""GPU diagnostic: where the end-to-end time of p_sample_loop goes (chunked vs step-by-step)."""
+import os, sys, time, types
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import livelyspeaker_b200 as ls
+from livelyspeaker_b200 import synthetic
+dev = torch.device("cuda:0")
+dims = synthetic.TED
+args = types.SimpleNamespace(mdm_condm='text', latent_dim=512, ff_size=1024, layers=8, cond_mask_prob=0.1, arch='trans_enc',
+                             emb_trans_dec=False, dataset='humanml', lang_model=None, mlpact='silu', diffusion_steps=1000,
+                             noise_schedule='cosine', sigma_small=True, lambda_vel=1.0, lambda_rcxyz=0.0, lambda_fc=0.0)
+B = 512
+model, diffusion = ls.create_model_and_diffusion(args, "")
+model.load_state_dict(synthetic.synth_state_dict(dims, seed=1))
+cfg = ls.ClassifierFreeSampleModel(model).to(dev).eval()
+eng = model.engine(B)
+y_host = synthetic.synth_cond(dims, B, seed=233)
+y_pin = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in y_host.items()}
+shape = (B, 9, 3, 34)
+
+def once(n, chunk):
+    diffusion.fused_chunk = chunk
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    yk = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in y_pin.items()}
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    out = diffusion.p_sample_loop(cfg, shape, clip_denoised=False, model_kwargs={"y": yk}, skip_timesteps=1000 - n)
+    t2 = time.perf_counter()
+    torch.cuda.synchronize(); t3 = time.perf_counter()
+    res = out.to("cpu")
+    t4 = time.perf_counter()
+    print("n=%d chunk=%d: h2d %.1f ms | loop enqueue %.1f ms | loop drain %.1f ms | d2h %.1f ms | total %.1f ms -> %.1f steps/s"
+          % (n, chunk, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3, (t4 - t0) * 1e3, n / (t4 - t0)))
+
+for n, chunk in ((200, 16), (200, 16), (200, 1), (200, 16), (32, 16), (1000, 16)):
+    once(n, chunk)
+y = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in y_host.items()}
+for _ in range(3):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    eng.set_cond(y, force=True)
+    torch.cuda.synchronize(); print("set_cond (WavEncoder + projections) %.2f ms" % ((time.perf_counter() - t0) * 1e3))
