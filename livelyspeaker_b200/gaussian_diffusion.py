@@ -475,11 +475,92 @@ class GaussianDiffusion:
                                              model_kwargs, device, progress, eta, skip_timesteps, init_image,
                                              randomize_class, cond_fn_with_grad, const_noise)
 
+    # ------------------------------------------------------------------ PLMS (generic route)
+    def plms_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                    cond_fn_with_grad=False, order=2, old_out=None):
+        """Pseudo linear multistep step (gaussian_diffusion.py:1016-1098 of the reference).  Runs on the generic
+        route: the denoiser is called through the C ABI (ls_cfg_forward), the multistep algebra is elementwise."""
+        if cond_fn_with_grad:
+            raise NotImplementedError("*_with_grad samplers are outside the sampling hot path (SURVEY.md 8f)")
+        if not int(order) or not 1 <= order <= 4:
+            raise ValueError('order is invalid (should be int from 1-4).')
+
+        def model_eps(x_, t_):
+            orig = self.p_mean_variance(model, x_, t_, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                        model_kwargs=model_kwargs)
+            out_ = orig if cond_fn is None else self.condition_score(cond_fn, orig, x_, t_, model_kwargs=model_kwargs)
+            return self._predict_eps_from_xstart(x_, t_, out_["pred_xstart"]), out_, orig
+
+        ab_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, x.shape)
+        eps, out, out_orig = model_eps(x, t)
+        if order > 1 and old_out is None:        # first step: pseudo improved Euler (second model call at t - 1)
+            old_eps = [eps]
+            mean_pred = out["pred_xstart"] * th.sqrt(ab_prev) + th.sqrt(1 - ab_prev) * eps
+            eps_2, _, _ = model_eps(mean_pred, t - 1)
+            eps_prime = (eps + eps_2) / 2
+        else:                                    # Adams-Bashforth; order 1 on the first step fails like the reference
+            old_eps = old_out["old_eps"]
+            old_eps.append(eps)
+            k = min(order, len(old_eps))
+            eps_prime = {1: lambda e: e[-1],
+                         2: lambda e: (3 * e[-1] - e[-2]) / 2,
+                         3: lambda e: (23 * e[-1] - 16 * e[-2] + 5 * e[-3]) / 12,
+                         4: lambda e: (55 * e[-1] - 59 * e[-2] + 37 * e[-3] - 9 * e[-4]) / 24}[k](old_eps)
+        pred_prime = self._predict_xstart_from_eps(x, t, eps_prime)
+        mean_pred = pred_prime * th.sqrt(ab_prev) + th.sqrt(1 - ab_prev) * eps_prime
+        if len(old_eps) >= order:
+            old_eps.pop(0)
+        nonzero_mask = (t != 0).float().view(-1, *([1] * (len(x.shape) - 1)))
+        sample = mean_pred * nonzero_mask + out["pred_xstart"] * (1 - nonzero_mask)
+        return {"sample": sample, "pred_xstart": out_orig["pred_xstart"], "old_eps": old_eps}
+
+    def plms_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
+                         randomize_class=False, cond_fn_with_grad=False, order=2):
+        final = None
+        for sample in self.plms_sample_loop_progressive(
+                model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+                model_kwargs=model_kwargs, device=device, progress=progress, skip_timesteps=skip_timesteps,
+                init_image=init_image, randomize_class=randomize_class, cond_fn_with_grad=cond_fn_with_grad,
+                order=order):
+            final = sample
+        return final["sample"]
+
+    def plms_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                     cond_fn=None, model_kwargs=None, device=None, progress=False, skip_timesteps=0,
+                                     init_image=None, randomize_class=False, cond_fn_with_grad=False, order=2):
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        img = noise if noise is not None else self.noise_source.randn(tuple(shape), device)
+        if skip_timesteps and init_image is None:
+            init_image = th.zeros_like(img)
+        indices = list(range(self.num_timesteps - skip_timesteps))[::-1]
+        if init_image is not None:
+            my_t = th.ones([shape[0]], device=device, dtype=th.long) * indices[0]
+            img = self.q_sample(init_image.to(device), my_t, img)
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        old_out = None
+        for i in indices:
+            t = th.tensor([i] * shape[0], device=device)
+            if randomize_class and 'y' in model_kwargs:
+                model_kwargs['y'] = th.randint(low=0, high=model.num_classes, size=model_kwargs['y'].shape,
+                                               device=model_kwargs['y'].device)
+            with th.no_grad():
+                out = self.plms_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                       cond_fn=cond_fn, model_kwargs=model_kwargs,
+                                       cond_fn_with_grad=cond_fn_with_grad, order=order, old_out=old_out)
+                yield out
+                old_out = out
+                img = out["sample"]
+
     # ------------------------------------------------------------------ out of scope
     def _out_of_scope(self, *a, **k):
-        raise NotImplementedError("training / VLB / PLMS / *_with_grad are outside the sampling hot path "
+        raise NotImplementedError("training / VLB / *_with_grad are outside the sampling hot path "
                                   "(SURVEY.md section 8f)")
 
-    training_losses = plms_sample = plms_sample_loop = plms_sample_loop_progressive = _out_of_scope
+    training_losses = _out_of_scope
     p_sample_with_grad = ddim_sample_with_grad = ddim_reverse_sample = _out_of_scope
     calc_bpd_loop = _vb_terms_bpd = _prior_bpd = _out_of_scope

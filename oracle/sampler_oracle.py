@@ -128,3 +128,57 @@ def sample_loop(sd, tab, tmap, shape, y, tape, ddim=False, eta=0.0, clip_denoise
         if trace is not None:
             trace.append((i, img, x0))
     return img
+
+
+def plms_loop(sd, tab, tmap, shape, y, tape, order=2, clip_denoised=False, skip_timesteps=0, init_image=None,
+              noise=None, trace=None):
+    """plms_sample_loop (gaussian_diffusion.py:1016-1211): pseudo improved Euler on the first step, then
+    Adams-Bashforth of the given order on the eps re-derived from the x0 prediction.  The first step calls the
+    model twice (second call at index i-1); no step noise is drawn.  order must be 2..4: with order 1 the
+    reference dereferences old_out=None on the first step (:1076)."""
+    B, nj, nf, _ = shape
+    n_t = len(tab["betas"])
+    img = noise if noise is not None else tape.draw(*shape)
+    if skip_timesteps and init_image is None:
+        init_image = torch.zeros_like(img)
+    indices = list(range(n_t - skip_timesteps))[::-1]
+    if init_image is not None:
+        img = q_sample(tab, init_image, indices[0], img)
+
+    def model_eps(x, i):
+        x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised)
+        eps = (_pick(tab["sqrt_recip_alphas_cumprod"], i) * x - x0) / _pick(tab["sqrt_recipm1_alphas_cumprod"], i)
+        return eps, x0
+
+    def x0_from_eps(x, i, eps):
+        return _pick(tab["sqrt_recip_alphas_cumprod"], i) * x - _pick(tab["sqrt_recipm1_alphas_cumprod"], i) * eps
+
+    old = None
+    for i in indices:
+        ab_prev = _pick(tab["alphas_cumprod_prev"], i)
+        eps, x0 = model_eps(img, i)
+        if order > 1 and old is None:
+            old = [eps]
+            mean = x0 * torch.sqrt(ab_prev) + torch.sqrt(1 - ab_prev) * eps
+            eps2, _ = model_eps(mean, i - 1)
+            eps_p = (eps + eps2) / 2
+        else:
+            old.append(eps)
+            k = min(order, len(old))
+            if k == 1:
+                eps_p = old[-1]
+            elif k == 2:
+                eps_p = (3 * old[-1] - old[-2]) / 2
+            elif k == 3:
+                eps_p = (23 * old[-1] - 16 * old[-2] + 5 * old[-3]) / 12
+            else:
+                eps_p = (55 * old[-1] - 59 * old[-2] + 37 * old[-3] - 9 * old[-4]) / 24
+        pred = x0_from_eps(img, i, eps_p)
+        mean = pred * torch.sqrt(ab_prev) + torch.sqrt(1 - ab_prev) * eps_p
+        if len(old) >= order:
+            old.pop(0)
+        nz = 0.0 if i == 0 else 1.0
+        img = mean * nz + x0 * (1 - nz)
+        if trace is not None:
+            trace.append((i, img, x0))
+    return img

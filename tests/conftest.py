@@ -38,5 +38,10 @@ def golden_beat():
 
 
 @pytest.fixture(scope="session")
+def golden_plms():
+    return dict(np.load(os.path.join(GOLDEN, "plms.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_schedule():
     return dict(np.load(os.path.join(GOLDEN, "schedule.npz")))

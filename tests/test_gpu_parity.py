@@ -11,7 +11,7 @@ import livelyspeaker_b200 as ls
 from conftest import ATOL, RTOL
 from livelyspeaker_b200 import beat_model_util, synthetic
 from oracle import rag_oracle, sampler_oracle, schedule_oracle
-from test_oracle_golden import LOOPS, run_oracle_loop
+from test_oracle_golden import LOOPS, PLMS, run_oracle_loop, run_oracle_plms
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -175,6 +175,26 @@ def test_whole_loop_beat(impl, golden_beat):
     got = diffusion.ddim_sample_loop(cfg, (2, 47, 6, 34), clip_denoised=False, model_kwargs={"y": y})
     _close(got, golden_beat["loop_ddim100"])
     _close(got, want)
+
+
+@pytest.mark.parametrize("tag", list(PLMS))
+def test_plms_loops_ted(tag, golden_plms):
+    """plms_sample_loop on the generic route - denoiser through ls_cfg_forward, multistep algebra
+    elementwise - against the reference's fixtures and the oracle on the recorded draws."""
+    spec, order, seed, kw = PLMS[tag]
+    kw = dict(kw)
+    dims, sd, cfg, diffusion = build("ted", spec)
+    want, tape = run_oracle_plms(tag, golden_plms, dims, sd)
+    init = torch.from_numpy(golden_plms["init_image"]).to(DEV) if kw.pop("init", False) else None
+    diffusion.noise_source = ls.ReplayNoise(tape.record)
+    got = diffusion.plms_sample_loop(cfg, (2, 9, 3, 34), model_kwargs={"y": synthetic.synth_cond(dims, 2, device=DEV)},
+                                     init_image=init, order=order, clip_denoised=kw.pop("clip_denoised", False), **kw)
+    _close(got, golden_plms["plms_" + tag])
+    _close(got, want)
+    with pytest.raises(ValueError):
+        diffusion.plms_sample(cfg, got, torch.zeros(2, dtype=torch.long, device=DEV), order=5)
+    with pytest.raises(NotImplementedError):
+        diffusion.plms_sample(cfg, got, torch.zeros(2, dtype=torch.long, device=DEV), cond_fn_with_grad=True)
 
 
 def test_same_seed_rng_order_and_layout_on_device():

@@ -5,6 +5,7 @@ import re
 import types
 
 import pytest
+import numpy as np
 import torch
 
 import livelyspeaker_b200 as ls
@@ -125,6 +126,36 @@ def test_generic_route_matches_reference_math_with_a_plain_model():
         nz = torch.randn_like(x)
         x = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp - sigma ** 2) * eps + (0.0 if i == 0 else 1.0) * sigma * nz
     assert torch.allclose(got, x, rtol=1e-6, atol=1e-6)
+
+
+def test_plms_host_logic_on_cpu_against_the_reference_fixture(golden_plms):
+    """PLMS is host logic over p_mean_variance.  Drive the product's plms_sample_loop on CPU with
+    a foreign model that evaluates the (reference-pinned) oracle denoiser: the result must be the reference's own
+    fixture, draws included (initial noise, then cond / uncond style per model call; no step noise)."""
+    from livelyspeaker_b200 import synthetic
+    from oracle import rag_oracle
+    dims = synthetic.TED
+    sd = synthetic.synth_state_dict(dims, seed=1)
+
+    class OracleCfg(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.anchor = torch.nn.Parameter(torch.zeros(1))      # gives the loop its device
+
+        def forward(self, x, t, y=None):
+            B = x.shape[0]
+            e_c, e_u = torch.randn(B, 1, 512), torch.randn(B, 1, 512)
+            return rag_oracle.cfg_forward(sd, x, t, y, e_c, e_u, dims.njoints, dims.nfeats)
+
+    d = ls.create_gaussian_diffusion(_args(), 'ddim100')
+    torch.manual_seed(304)
+    with torch.no_grad():
+        got = d.plms_sample_loop(OracleCfg(), (2, 9, 3, 34), clip_denoised=False,
+                                 model_kwargs={"y": synthetic.synth_cond(dims, 2)}, skip_timesteps=80,
+                                 init_image=torch.from_numpy(golden_plms["init_image"]), order=2)
+    np.testing.assert_allclose(got.numpy(), golden_plms["plms_ddim100_o2_sdedit"], rtol=1e-5, atol=2e-5)
+    with pytest.raises(TypeError):       # order 1 dereferences old_out=None on the first step, as in the reference
+        d.plms_sample(OracleCfg(), got, torch.zeros(2, dtype=torch.long), order=1, model_kwargs={"y": synthetic.synth_cond(dims, 2)})
 
 
 def test_product_never_imports_oracle_or_reference():

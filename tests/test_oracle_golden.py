@@ -122,6 +122,34 @@ def test_whole_loops_ted(tag, golden_ted, ted):
     np.testing.assert_allclose(out.numpy(), golden_ted["loop_" + tag], rtol=RTOL, atol=ATOL)
 
 
+PLMS = {   # tag: (respacing, order, seed, kwargs) - tests/golden/make_golden_plms.py
+    "ddim100_o2": ("ddim100", 2, 301, {}),
+    "ddim100_o3": ("ddim100", 3, 302, {}),
+    "ddim50_o4_clip": ("ddim50", 4, 303, {"clip_denoised": True}),
+    "ddim100_o2_sdedit": ("ddim100", 2, 304, {"skip_timesteps": 80, "init": True}),
+}
+
+
+def run_oracle_plms(tag, g, dims, sd):
+    spec, order, seed, kw = PLMS[tag]
+    kw = dict(kw)
+    tab, tmap = schedule_oracle.build("cosine", 1000, spec)
+    init = torch.from_numpy(g["init_image"]) if kw.pop("init", False) else None
+    tape = sampler_oracle.NoiseTape(seed=seed)
+    with torch.no_grad():
+        out = sampler_oracle.plms_loop(sd, tab, tmap, (2, dims.njoints, dims.nfeats, 34), synthetic.synth_cond(dims, 2),
+                                       tape, order=order, init_image=init, **kw)
+    return out, tape
+
+
+@pytest.mark.parametrize("tag", ["ddim100_o3", "ddim50_o4_clip", "ddim100_o2_sdedit"])
+def test_plms_loops_ted(tag, golden_plms, ted):
+    """PLMS (reference gaussian_diffusion.py:1016-1211): the oracle against the reference's own outputs."""
+    dims, sd = ted
+    out, _ = run_oracle_plms(tag, golden_plms, dims, sd)
+    _close(out, golden_plms["plms_" + tag])
+
+
 def test_whole_loop_beat(golden_beat):
     dims = synthetic.BEAT
     sd = synthetic.synth_state_dict(dims, seed=1)
