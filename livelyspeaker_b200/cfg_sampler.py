@@ -18,6 +18,9 @@ class ClassifierFreeSampleModel(nn.Module):
         self.nfeats = model.nfeats
         self.data_rep = model.data_rep
         self.cond_mode = model.cond_mode
+        # Optional source of the two style draws of a call (an object with randn(shape, device), e.g. the
+        # ReplayNoise a test shares with the diffusion); None = torch's generator, like the reference.
+        self.noise_source = None
 
     def forward(self, x, timesteps, y=None):
         # cfg_sampler.py:25: a model trained without condition dropout falls through and
@@ -31,6 +34,10 @@ class ClassifierFreeSampleModel(nn.Module):
         eng = inner.engine(bs)
         eng.set_cond(y)
         # draw order of the reference: cond pass first, then the uncond pass
-        eps_c = torch.randn(bs, 1, inner.latent_dim, device=eng.device)
-        eps_u = torch.randn(bs, 1, inner.latent_dim, device=eng.device)
+        if self.noise_source is not None:
+            eps_c = self.noise_source.randn((bs, 1, inner.latent_dim), eng.device)
+            eps_u = self.noise_source.randn((bs, 1, inner.latent_dim), eng.device)
+        else:
+            eps_c = torch.randn(bs, 1, inner.latent_dim, device=eng.device)
+            eps_u = torch.randn(bs, 1, inner.latent_dim, device=eng.device)
         return eng.cfg_forward(x, timesteps, eps_c, eps_u, y['scale'])

@@ -137,6 +137,7 @@ extern "C" void ls_destroy(ls_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   lsf_destroy(h);
+  lsw_destroy(h);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -236,6 +237,11 @@ extern "C" int ls_finalize_weights(ls_handle* h, void* stream) {
                                  R(te + "time_embed.2.bias"), const_cast<float*>(h->w.emb_table), h->cfg.max_timestep, s)))
     return rc;
   if ((rc = lsf_init(h, s)) < 0) return rc;
+  if (rc == 0) {      // tcgen05 path available: the WavEncoder's three wide convolutions run on the tensor cores too
+    const float* wc[3] = {R("audio_encoder.feat_extractor.3.weight"), R("audio_encoder.feat_extractor.6.weight"),
+                          R("audio_encoder.feat_extractor.9.weight")};
+    if ((rc = lsw_init(h, wc, s)) < 0) return rc;
+  }
   h->finalized = true;
   h->cond_batch = 0;
   return LS_OK;

@@ -78,6 +78,7 @@ struct ls_handle {
   float* w2_t = nullptr;    // time_embed.2.weight^T
   int wav_chunk = 0;
   void* fused = nullptr;    // state of the tcgen05 path (ls_fused.cu)
+  void* wavtc = nullptr;    // state of the tcgen05 WavEncoder convolutions (ls_wavenc_tc.cu)
 };
 
 int ls_fail(ls_handle* h, int code, const char* fmt, ...);
@@ -116,6 +117,12 @@ int lsk_cfg_update(ls_handle* h, int B, const ls_step_params* p, const float* ou
                    float* x_prev, float* pred_x0, cudaStream_t s);
 int lsk_axpby(ls_handle* h, int64_t n, const float* a, const float* b, float ca, float cb, float* out,
               cudaStream_t s);
+// ls_wavenc_tc.cu
+int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s);
+void lsw_destroy(ls_handle* h);
+int lsw_available(const ls_handle* h);
+int lsw_conv(ls_handle* h, int layer, const float* in, const float* bias, float* out, int nb, int Li, int Lo,
+             cudaStream_t s);
 // ls_fused.cu
 int lsf_init(ls_handle* h, cudaStream_t s);            // build bf16 weight tapes; 0 if available
 void lsf_destroy(ls_handle* h);

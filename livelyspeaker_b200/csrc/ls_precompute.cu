@@ -130,6 +130,8 @@ int lsk_wav_encoder(ls_handle* h, int B, const float* audio, float* out_cm, cuda
   const float *w1 = W("audio_encoder.feat_extractor.3.weight"), *b1 = W("audio_encoder.feat_extractor.3.bias");
   const float *w2 = W("audio_encoder.feat_extractor.6.weight"), *b2 = W("audio_encoder.feat_extractor.6.bias");
   const float *w3 = W("audio_encoder.feat_extractor.9.weight"), *b3 = W("audio_encoder.feat_extractor.9.bias");
+  // layers 2-4 on the tensor cores (bf16x3) unless the exact-order fp32 implementation is selected
+  const bool tc = lsw_available(h) && ls_get_impl(h) != LS_IMPL_SIMT;
   for (int c0 = 0; c0 < B; c0 += h->wav_chunk) {
     const int nb = min(h->wav_chunk, B - c0);
     const float* a = audio + (size_t)c0 * L0;
@@ -137,17 +139,30 @@ int lsk_wav_encoder(ls_handle* h, int B, const float* audio, float* out_cm, cuda
     LS_LAUNCH_CHECK(h);
     instnorm_lrelu_kernel<<<nb * 32, 256, 0, s>>>(h->wav_a, L1);
     LS_LAUNCH_CHECK(h);
-    conv1d_k15_kernel<6><<<dim3((L2 + CV_TL - 1) / CV_TL, 2, nb), 128, 0, s>>>(h->wav_a, w1, b1, h->wav_b, 32, L1, 64, L2, 0);
-    LS_LAUNCH_CHECK(h);
+    float* out4 = out_cm + (size_t)c0 * LS_AF * LS_F;
+    int rc;
+    if (tc) {
+      if ((rc = lsw_conv(h, 0, h->wav_a, b1, h->wav_b, nb, L1, L2, s))) return rc;
+    } else {
+      conv1d_k15_kernel<6><<<dim3((L2 + CV_TL - 1) / CV_TL, 2, nb), 128, 0, s>>>(h->wav_a, w1, b1, h->wav_b, 32, L1, 64, L2, 0);
+      LS_LAUNCH_CHECK(h);
+    }
     instnorm_lrelu_kernel<<<nb * 64, 256, 0, s>>>(h->wav_b, L2);
     LS_LAUNCH_CHECK(h);
-    conv1d_k15_kernel<6><<<dim3((L3 + CV_TL - 1) / CV_TL, 4, nb), 128, 0, s>>>(h->wav_b, w2, b2, h->wav_a, 64, L2, 128, L3, 0);
-    LS_LAUNCH_CHECK(h);
+    if (tc) {
+      if ((rc = lsw_conv(h, 1, h->wav_b, b2, h->wav_a, nb, L2, L3, s))) return rc;
+    } else {
+      conv1d_k15_kernel<6><<<dim3((L3 + CV_TL - 1) / CV_TL, 4, nb), 128, 0, s>>>(h->wav_b, w2, b2, h->wav_a, 64, L2, 128, L3, 0);
+      LS_LAUNCH_CHECK(h);
+    }
     instnorm_lrelu_kernel<<<nb * 128, 256, 0, s>>>(h->wav_a, L3);
     LS_LAUNCH_CHECK(h);
-    conv1d_k15_kernel<6><<<dim3((L4 + CV_TL - 1) / CV_TL, 8, nb), 128, 0, s>>>(
-        h->wav_a, w3, b3, out_cm + (size_t)c0 * LS_AF * LS_F, 128, L3, 256, L4, 0);
-    LS_LAUNCH_CHECK(h);
+    if (tc) {
+      if ((rc = lsw_conv(h, 2, h->wav_a, b3, out4, nb, L3, L4, s))) return rc;
+    } else {
+      conv1d_k15_kernel<6><<<dim3((L4 + CV_TL - 1) / CV_TL, 8, nb), 128, 0, s>>>(h->wav_a, w3, b3, out4, 128, L3, 256, L4, 0);
+      LS_LAUNCH_CHECK(h);
+    }
   }
   return LS_OK;
 }

@@ -186,7 +186,7 @@ def test_plms_loops_ted(tag, golden_plms):
     dims, sd, cfg, diffusion = build("ted", spec)
     want, tape = run_oracle_plms(tag, golden_plms, dims, sd)
     init = torch.from_numpy(golden_plms["init_image"]).to(DEV) if kw.pop("init", False) else None
-    diffusion.noise_source = ls.ReplayNoise(tape.record)
+    diffusion.noise_source = cfg.noise_source = ls.ReplayNoise(tape.record)     # one tape: loop draws + style draws
     got = diffusion.plms_sample_loop(cfg, (2, 9, 3, 34), model_kwargs={"y": synthetic.synth_cond(dims, 2, device=DEV)},
                                      init_image=init, order=order, clip_denoised=kw.pop("clip_denoised", False), **kw)
     _close(got, golden_plms["plms_" + tag])
