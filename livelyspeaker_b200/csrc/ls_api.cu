@@ -111,7 +111,7 @@ extern "C" int ls_create(ls_handle** out, const ls_config* cfg) {
   for (auto& r : h->raw)
     if ((rc = dev_alloc_t(h, &r.dev, (size_t)r.numel)) != LS_OK) break;
   const size_t MB = cfg->max_batch;
-  h->wav_chunk = (int)std::min<size_t>(MB, 64);
+  h->wav_chunk = (int)std::min<size_t>(MB, 512);   // clips per WavEncoder pass: 0.7 GB of workspace at 512, grids that fill the GPU
   const size_t L1 = (cfg->audio_len + 3200 - 15) / 5 + 1, L2 = (L1 - 15) / 6 + 1, L3 = (L2 - 15) / 6 + 1;
   if (rc == LS_OK) rc = dev_alloc_t(h, &h->A, MB * LS_F * LS_D);
   if (rc == LS_OK) rc = dev_alloc_t(h, &h->P, MB * LS_F * LS_D);
