@@ -177,6 +177,43 @@ int ls_step_multi(ls_handle* h, int32_t B, int32_t n_steps, const ls_step_params
 int ls_q_sample(ls_handle* h, int64_t n, const float* x0, const float* noise,
                 float c_x0, float c_noise, float* out, void* stream);
 
+/* ---- SAG decoder ------------------------------------------------
+ * Decoder_TRANSFORMER.forward (scripts/model/motionclip_module.py:137-183): the CLIP text
+ * feature z -> coarse motion that LivelySpeaker sampling uses as init_image
+ * (scripts/test_LivelySpeaker_ted.py:80-113).  Stateless: the caller passes device pointers
+ * to the weights, the matrices TRANSPOSED ([in][out], contiguous) so that the kernel reads
+ * them coalesced; biases / LayerNorm vectors as in the state_dict.                      */
+#define LS_SAG_MAX_LAYERS 8
+typedef struct ls_sag_layer {
+  const float* sa_in_wt;   /* self_attn.in_proj_weight^T        [512][1536] */
+  const float* sa_in_b;    /* self_attn.in_proj_bias            [1536]      */
+  const float* sa_out_wt;  /* self_attn.out_proj.weight^T       [512][512]  */
+  const float* sa_out_b;
+  const float* ca_v_wt;    /* multihead_attn.in_proj_weight[1024:1536]^T [512][512] (the memory is one token) */
+  const float* ca_v_b;     /* multihead_attn.in_proj_bias[1024:1536]               */
+  const float* ca_out_wt;  /* multihead_attn.out_proj.weight^T  [512][512]  */
+  const float* ca_out_b;
+  const float* l1_wt;      /* linear1.weight^T                  [512][1024] */
+  const float* l1_b;
+  const float* l2_wt;      /* linear2.weight^T                  [1024][512] */
+  const float* l2_b;
+  const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b;   /* norm1..3 weight / bias [512] */
+} ls_sag_layer;
+typedef struct ls_sag_weights {
+  int32_t n_layers, njoints, nfeats, n_frames, n_pre_poses, latent_dim, ff_size, n_heads;
+  const float* map_wt;     /* mapping.weight^T                  [J*D+1][512] */
+  const float* map_b;
+  const float* pe;         /* sequence_pos_encoder.pe rows 0..n_frames-1, row stride pe_stride floats */
+  int64_t pe_stride;
+  const float* fin_wt;     /* finallayer.weight^T               [512][J*D]  */
+  const float* fin_b;
+  ls_sag_layer layer[LS_SAG_MAX_LAYERS];
+} ls_sag_weights;
+/* x [B,J*D,F] (frames >= n_pre_poses are ignored), z [B,512], mask [B,F] bytes (0 = padded,
+ * may be NULL) -> out [B,J*D,F].  Errors: ls_last_error(NULL).                           */
+int ls_sag_decode(const ls_sag_weights* w, int32_t B, const float* x, const float* z,
+                  const uint8_t* mask, float* out, void* stream);
+
 /* Introspection used by tests / bench: number of kernels launched by this handle
  * since creation, and read-back of the step-invariant buffers.                    */
 int64_t ls_launch_count(const ls_handle* h);

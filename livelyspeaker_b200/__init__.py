@@ -10,7 +10,8 @@ from .gaussian_diffusion import GaussianDiffusion, LossType, ModelMeanType, Mode
 from .model_util import create_gaussian_diffusion, create_model_and_diffusion, get_model_args, load_model_wo_clip
 from .rag import RAG
 from .respace import SpacedDiffusion, space_timesteps
+from .sag import Decoder_TRANSFORMER
 
 __all__ = ["ClassifierFreeSampleModel", "GaussianDiffusion", "LossType", "ModelMeanType", "ModelVarType",
            "ReplayNoise", "TorchNoise", "create_gaussian_diffusion", "create_model_and_diffusion",
-           "get_model_args", "load_model_wo_clip", "RAG", "SpacedDiffusion", "space_timesteps"]
+           "get_model_args", "load_model_wo_clip", "RAG", "SpacedDiffusion", "space_timesteps", "Decoder_TRANSFORMER"]

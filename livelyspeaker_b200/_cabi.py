@@ -19,7 +19,7 @@ IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
-           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_q_sample", "ls_launch_count",
+           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_q_sample", "ls_launch_count",
            "ls_debug_buffer"]
 
 

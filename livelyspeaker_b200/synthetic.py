@@ -113,6 +113,41 @@ def synth_state_dict(dims=TED, seed=1):
     return sd
 
 
+def synth_sag_state_dict(seed=3, njoints=9, nfeats=3, d=512, ff=1024, layers=3):
+    """Deterministic fp32 state_dict with the key set of the reference's SAG decoder
+    (scripts/model/motionclip_module.py:98-134: nn.TransformerDecoder, 3 layers, + mapping / finallayer / pe)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def uni(shape, fan_in):
+        b = 1.0 / math.sqrt(fan_in)
+        return (torch.rand(shape, generator=g) * 2 - 1) * b
+
+    def nrm(shape, std):
+        return torch.randn(shape, generator=g) * std
+
+    jd = njoints * nfeats
+    sd = {"sequence_pos_encoder.pe": positional_table(d)}
+    for l in range(layers):
+        p = "seqTransDecoder.layers.%d." % l
+        for a in ("self_attn.", "multihead_attn."):
+            sd[p + a + "in_proj_weight"] = uni((3 * d, d), d) * math.sqrt(3.0)
+            sd[p + a + "in_proj_bias"] = nrm((3 * d,), 0.02)
+            sd[p + a + "out_proj.weight"] = uni((d, d), d)
+            sd[p + a + "out_proj.bias"] = nrm((d,), 0.02)
+        sd[p + "linear1.weight"] = uni((ff, d), d)
+        sd[p + "linear1.bias"] = uni((ff,), d)
+        sd[p + "linear2.weight"] = uni((d, ff), ff)
+        sd[p + "linear2.bias"] = uni((d,), ff)
+        for n in ("norm1", "norm2", "norm3"):
+            sd[p + n + ".weight"] = 1 + nrm((d,), 0.1)
+            sd[p + n + ".bias"] = nrm((d,), 0.1)
+    sd["finallayer.weight"] = uni((jd, d), d)
+    sd["finallayer.bias"] = uni((jd,), d)
+    sd["mapping.weight"] = uni((d, jd + 1), jd + 1)
+    sd["mapping.bias"] = uni((d,), jd + 1)
+    return sd
+
+
 def synth_cond(dims, batch, seed=233, scale=1.5, device="cpu"):
     """The `y` dict the eval scripts build (scripts/test_RAG_ted.py:63-70,
     scripts_beat/test_RAG_beat.py:100-125), synthetic values."""

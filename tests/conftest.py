@@ -43,5 +43,10 @@ def golden_plms():
 
 
 @pytest.fixture(scope="session")
+def golden_sag():
+    return dict(np.load(os.path.join(GOLDEN, "sag.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_schedule():
     return dict(np.load(os.path.join(GOLDEN, "schedule.npz")))

@@ -197,6 +197,40 @@ def test_plms_loops_ted(tag, golden_plms):
         diffusion.plms_sample(cfg, got, torch.zeros(2, dtype=torch.long, device=DEV), cond_fn_with_grad=True)
 
 
+def test_sag_decoder(golden_sag):
+    """Decoder_TRANSFORMER.forward through ls_sag_decode against the reference module's fixture and the oracle;
+    then config-3 style use: its output as init_image of a RAG loop, B=256 batch independence."""
+    from oracle import sag_oracle
+    sd = synthetic.synth_sag_state_dict(seed=3)
+    dec = ls.Decoder_TRANSFORMER(latent_dim=512, n_pre_poses=4, use_style=False)
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.to(DEV).eval()
+    x, z, mask = (torch.from_numpy(golden_sag[k]) for k in ("x", "z", "mask"))
+    batch = dec({"x": x.to(DEV), "z": z.to(DEV), "mask": mask.to(DEV)})
+    assert set(batch) >= {"output", "final_z"} and batch["output"].shape == (3, 9, 3, 34)
+    _close(batch["output"], golden_sag["output"])
+    with torch.no_grad():
+        _close(batch["output"], sag_oracle.decode(sd, x, z, mask))
+    assert float(batch["output"][1, :, :, 30:].abs().max()) == 0.0
+    # B = 256 (BASELINE config 3): clip b of the big batch == the same clip alone, and vs the oracle on 2 clips
+    g = torch.Generator().manual_seed(8)
+    B = 256
+    xb, zb = 0.3 * torch.randn(B, 9, 3, 34, generator=g), torch.randn(B, 512, generator=g)
+    mb = torch.ones(B, 34, dtype=torch.bool)
+    big = dec({"x": xb.to(DEV), "z": zb.to(DEV), "mask": mb.to(DEV)}, use_text_emb=False)["output"]
+    idx = [0, 255]
+    small = dec({"x": xb[idx].to(DEV), "z": zb[idx].to(DEV), "mask": mb[idx].to(DEV)})["output"]
+    assert torch.equal(big[idx], small)
+    with torch.no_grad():
+        _close(small, sag_oracle.decode(sd, xb[idx], zb[idx], mb[idx]))
+    # its output drives the RAG loop as init_image (scripts/test_LivelySpeaker_ted.py:88-113)
+    dims, _, cfg, diffusion = build("ted", "ddim100")
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    out = diffusion.ddim_sample_loop(cfg, (2, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=80,
+                                     init_image=small)
+    assert out.shape == (2, 9, 3, 34) and torch.isfinite(out).all()
+
+
 def test_same_seed_rng_order_and_layout_on_device():
     """Draw order + memory layout parity: with the oracle's tape drawing from the CUDA
     generator, the product's own torch draws under the same seed must be identical."""

@@ -158,6 +158,22 @@ def test_plms_host_logic_on_cpu_against_the_reference_fixture(golden_plms):
         d.plms_sample(OracleCfg(), got, torch.zeros(2, dtype=torch.long), order=1, model_kwargs={"y": synthetic.synth_cond(dims, 2)})
 
 
+def test_sag_decoder_surface_and_no_cpu_path():
+    """Same state_dict key set / shapes as the reference's Decoder_TRANSFORMER (the synthetic dict loads strictly
+    into the reference module, tests/golden/make_golden_sag.py) and no CPU implementation behind it."""
+    from livelyspeaker_b200 import synthetic
+    from livelyspeaker_b200._cabi import LsError
+    dec = ls.Decoder_TRANSFORMER(latent_dim=512, n_pre_poses=4, use_style=False).eval()
+    sd = synthetic.synth_sag_state_dict(seed=3)
+    assert {k: tuple(v.shape) for k, v in dec.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    dec.load_state_dict(sd, strict=True)
+    batch = {"x": torch.zeros(2, 9, 3, 34), "z": torch.zeros(2, 512), "mask": torch.ones(2, 34, dtype=torch.bool)}
+    with pytest.raises(LsError):
+        dec(batch)
+    with pytest.raises(NotImplementedError):
+        dec.train()(batch)
+
+
 def test_product_never_imports_oracle_or_reference():
     pkg = os.path.join(ROOT, "livelyspeaker_b200")
     pat = re.compile(r"^\s*(from|import)\s+(oracle|tests)\b|/root/reference", re.M)

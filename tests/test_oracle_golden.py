@@ -150,6 +150,20 @@ def test_plms_loops_ted(tag, golden_plms, ted):
     _close(out, golden_plms["plms_" + tag])
 
 
+def test_sag_decoder(golden_sag):
+    """SAG decoder: the oracle against the reference module's own output
+    (tests/golden/make_golden_sag.py: nn.TransformerDecoder of the reference tree)."""
+    from oracle import sag_oracle
+    sd = synthetic.synth_sag_state_dict(seed=3)
+    s = sum(float(v.double().abs().sum()) for v in sd.values())
+    assert abs(s - float(golden_sag["weights_abs_sum"])) < 1e-6 * s
+    with torch.no_grad():
+        out = sag_oracle.decode(sd, torch.from_numpy(golden_sag["x"]), torch.from_numpy(golden_sag["z"]),
+                                torch.from_numpy(golden_sag["mask"]))
+    _close(out, golden_sag["output"])
+    assert float(out[1, :, :, 30:].abs().max()) == 0.0        # padded frames are zeroed
+
+
 def test_whole_loop_beat(golden_beat):
     dims = synthetic.BEAT
     sd = synthetic.synth_state_dict(dims, seed=1)

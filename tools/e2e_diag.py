@@ -38,3 +38,20 @@ for _ in range(3):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     eng.set_cond(y, force=True)
     torch.cuda.synchronize(); print("set_cond (WavEncoder + projections) %.2f ms" % ((time.perf_counter() - t0) * 1e3))
+
+# SAG decoder (config 3 front end): time at B=256
+dec = ls.Decoder_TRANSFORMER(latent_dim=512, n_pre_poses=4, use_style=False)
+dec.load_state_dict(synthetic.synth_sag_state_dict(seed=3))
+dec = dec.to(dev).eval()
+g = torch.Generator().manual_seed(8)
+for Bs in (256, 512):
+    batch = {"x": (0.3 * torch.randn(Bs, 9, 3, 34, generator=g)).to(dev), "z": torch.randn(Bs, 512, generator=g).to(dev),
+             "mask": torch.ones(Bs, 34, dtype=torch.bool, device=dev)}
+    dec(dict(batch)); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        dec(dict(batch))
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print("SAG decode B=%d: %.2f ms  (%.1f TFLOP/s fp32 algorithmic at 438 MFLOP/clip)" % (Bs, ms, Bs * 438e6 / ms / 1e9))
