@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <cstddef>
+
 #include "ls_internal.cuh"
 
 static std::string g_create_error;
@@ -324,6 +326,9 @@ extern "C" int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int
   if ((rc = lsk_denoise_simt(h, B, x, t, -1, 3, eps_cond, eps_uncond, h->out_c, h->out_u, s))) return rc;
   return lsk_cfg_combine(h, B, h->out_c, h->out_u, scale, out, s);
 }
+
+static_assert(sizeof(ls_step_params) == 48 && sizeof(ls_step_io) == 64 && offsetof(ls_step_io, x_prev) == 48,
+              "ls_step_params / ls_step_io layouts are part of the ABI (livelyspeaker_b200/_cabi.py mirrors them)");
 
 static int check_step(ls_handle* h, const ls_step_params* p, const ls_step_io* io, bool allow_mode2) {
   if (p->mode < 0 || p->mode > (allow_mode2 ? 2 : 1)) return ls_fail(h, LS_EINVAL, "mode %d", p->mode);

@@ -9,7 +9,12 @@
 // hidden half), all [34][512] fp32.  Every projection is "thread = output column, 34 accumulators in registers",
 // reading the token rows as broadcast float4 and the TRANSPOSED weights ([k][n], prepared by the host mirror)
 // coalesced; out-projection and FFN-2 accumulate across heads / hidden halves in registers.
+#include <cstddef>
+
 #include "ls_internal.cuh"
+
+static_assert(sizeof(ls_sag_layer) == 144 && sizeof(ls_sag_weights) == 1232 && offsetof(ls_sag_weights, layer) == 80,
+              "ls_sag_weights layout is part of the ABI (livelyspeaker_b200/sag.py mirrors it)");
 
 namespace {
 

@@ -9,6 +9,10 @@
 //           (token-mix weights), M=128 N=80 K=80, LBO = channel-block stride, SBO = 1024
 //   case 3: as 2 with LBO / SBO swapped (to learn which reading of the ISA is right)
 //   case 4: case 0 with K split over two 64-channel blocks + accumulate flag (K=128)
+//   case 6: A operand from TENSOR MEMORY (TS mode, for a token-mix GEMM that keeps LayerNorm-1's output out of
+//           shared memory): lane = M row, 32-bit column j = (k = 2j in the low half, k = 2j+1 in the high half),
+//           8 columns per K=16 step, written with tcgen05.st.32x32b; B K-major from shared memory; M=128 N=80 K=64
+//   case 7: as 6 with the halves swapped (to learn the packing if 6 fails)
 //   case 5: the concatenated operand of the fused kernel: B = 144 contiguous rows (lo image rows
 //           0..71 then hi image rows 0..71), one N=144 MMA per K step into D at column 152 (8- but not
 //           16-aligned), then N=80 MMAs from row 72 accumulating into D + 72 (column 224)
@@ -59,6 +63,23 @@ probe_kernel(int which, const __nv_bfloat16* __restrict__ u_g /*[80][128]*/, con
     uint8_t* dst = (k < 64) ? s.wt : s.wt2;
     *reinterpret_cast<__nv_bfloat16*>(dst + tile_off(n, k & 63, 0)) = v;
   }
+  if (which == 6 || which == 7) {     // A[m][k] = W[m][k], k < 64, packed bf16 pairs into TMEM columns 256..287 of lane m
+    __syncthreads();
+    const uint32_t tm = s.tmem_base;
+    uint32_t r[32];
+    for (int j = 0; j < 32; ++j) {
+      const float a0 = (float)((tid * 2 + (2 * j) * 3) % 5 - 2), a1 = (float)((tid * 2 + (2 * j + 1) * 3) % 5 - 2);
+      const uint32_t b0 = __float_as_uint(a0) >> 16, b1 = __float_as_uint(a1) >> 16;      // exact bf16 of small integers
+      r[j] = (which == 6) ? (b0 | (b1 << 16)) : (b1 | (b0 << 16));
+    }
+    for (int c0 = 0; c0 < 32; c0 += 8)
+      asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(
+                       tm + ((uint32_t)(warp * 32) << 16) + 256 + c0),
+                   "r"(r[c0]), "r"(r[c0 + 1]), "r"(r[c0 + 2]), "r"(r[c0 + 3]), "r"(r[c0 + 4]), "r"(r[c0 + 5]), "r"(r[c0 + 6]),
+                   "r"(r[c0 + 7])
+                   : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
   if (which == 5) {       // 160 rows x 64 channels, one block: row r = u_g row (r % 80), channel c -> c + 64*(r / 80)
     __syncthreads();
     for (int i = tid; i < 160 * 64; i += 128) {
@@ -87,6 +108,18 @@ probe_kernel(int which, const __nv_bfloat16* __restrict__ u_g /*[80][128]*/, con
           uint64_t bd = smem_desc(smem_u32(s.u) + b * CB_STRIDE + ks * 32, 16, 1024, SWZ_128B);
           umma_bf16(tmem + dcol, ad, bd, id, (b | ks) ? 1u : 0u);
         }
+    } else if (which == 6 || which == 7) {
+      const uint32_t id = idesc_bf16(128, 80, 0, 0);
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        uint64_t bd = smem_desc(smem_u32(s.u) + ks * 32, 16, 1024, SWZ_128B);
+        const uint32_t a_t = tmem + 256 + ks * 8, acc = ks ? 1u : 0u;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+            ::"r"(tmem + dcol), "r"(a_t), "l"(bd), "r"(id), "r"(acc)
+            : "memory");
+      }
     } else if (which == 5) {
       mbar_arrive_expect_tx(&s.bar_w, 16384);
       bulk_g2s(s.w, w_img, 16384, &s.bar_w);
@@ -174,7 +207,8 @@ int main() {
   const int smem = sizeof(Smem) + 1024;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int bad_total = 0;
-  for (int which = 0; which < 5; ++which) {
+  for (int which = 0; which < 8; ++which) {
+    if (which == 5) continue;     // checked separately below
     cudaMemset(dD, 0xff, 128 * 80 * 4);
     probe_kernel<<<1, 128, smem>>>(which, (const __nv_bfloat16*)dU, (const uint8_t*)dW, (const __nv_bfloat16*)dWT, dD);
     cudaError_t e = cudaDeviceSynchronize();
@@ -189,7 +223,7 @@ int main() {
     for (int m = 0; m < 128; ++m)
       for (int n = 0; n < 80; ++n) {
         double ref = 0;
-        if (which == 0 || which == 1 || which == 4) {
+        if (which == 0 || which == 1 || which == 4 || which >= 6) {
           int K = (which == 4) ? 128 : 64;
           for (int k = 0; k < K; ++k) ref += (double)W[m * 128 + k] * U[n * NCH + k];
         } else {
@@ -201,7 +235,7 @@ int main() {
       }
     printf("case %d: mismatches %d / %d, max err %g  (D[0][0..3] = %g %g %g %g)\n", which, bad, 128 * 80, maxerr, D[0],
            D[1], D[2], D[3]);
-    if (which != 3) bad_total += bad;
+    if (which != 3 && which != 7) bad_total += bad;      // 3 and 7 are the "other reading" probes
   }
   {
     cudaMemset(dD, 0xff, 128 * 144 * 4);

@@ -34,6 +34,11 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_cabi.LsConfig) == 12 * 4
     assert ctypes.sizeof(_cabi.LsStepParams) == 4 * 4 + 8 * 4
     assert _cabi.LsStepParams.c.offset == 16
+    assert ctypes.sizeof(_cabi.LsStepIO) == 64 and _cabi.LsStepIO.x_prev.offset == 48      # static_assert'ed in ls_api.cu
+    from livelyspeaker_b200 import sag
+    assert ctypes.sizeof(sag.LsSagLayer) == 18 * 8
+    assert ctypes.sizeof(sag.LsSagWeights) == 8 * 4 + 6 * 8 + sag.SAG_MAX_LAYERS * 18 * 8 == 1232   # ... in ls_sag.cu
+    assert sag.LsSagWeights.layer.offset == 80
 
 
 def test_create_fails_loudly_without_gpu():
