@@ -124,6 +124,45 @@ def cpu_port_steps_per_s(dims, batch_equiv, n_steps, warmup, sample_batch, threa
     return (sample_batch / batch_equiv) / per_step, per_step
 
 
+def gpu_eager_port_steps_per_s(dims, batch, n_steps, dev):
+    """The same oracle port run as eager PyTorch on the GPU (fp32, TF32 off): the honest "reference code on a B200"
+    comparator of SURVEY.md 8d (the reference tree itself is not on the GPU box).  A reported baseline only."""
+    import torch
+    from livelyspeaker_b200 import synthetic
+    from oracle import sampler_oracle, schedule_oracle
+    sd = {k: v.to(dev) for k, v in synthetic.synth_state_dict(dims, seed=1).items()}
+    tab, tmap = schedule_oracle.build("cosine", T_FULL, "")
+    y = synthetic.synth_cond(dims, batch, device=dev)
+
+    class DevTape(sampler_oracle.NoiseTape):
+        def __init__(self):
+            self.replay, self.record, self.gen, self.device = None, [], None, dev
+
+        def draw(self, *s_):
+            return torch.randn(*s_, device=dev)
+
+        def draw_like(self, x_):
+            return torch.randn_like(x_)
+
+    pick, tf32 = sampler_oracle._pick, (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    sampler_oracle._pick = lambda table, i: pick(table, i).to(dev)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        tape = DevTape()
+        x = tape.draw(batch, dims.njoints, dims.nfeats, 34)
+        with torch.no_grad():
+            for k in range(2 + n_steps):
+                if k == 2:
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                x, _ = sampler_oracle.p_sample_step(sd, tab, tmap, x, T_FULL - 1 - k, y, tape, dims.njoints, dims.nfeats)
+            torch.cuda.synchronize(dev)
+        return n_steps / (time.perf_counter() - t0)
+    finally:
+        sampler_oracle._pick = pick
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+
 def run_reference_arm(a, dims, rank):
     """--impl reference: the reference's own CPU implementation of the path.  The reference
     tree is not present on the GPU box, so this times oracle/ (kind "port"), which is
@@ -357,6 +396,13 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": threads, "kind": "port",
                                     "sample": "4 oracle p_sample steps at B=%d clips (CFG on, WavEncoder recomputed "
                                               "per step as in the reference), %.3f s each, scaled to B=%d" % (sb, per, B)}
+            try:
+                line["gpu_eager_baseline"] = {
+                    "value": gpu_eager_port_steps_per_s(dims, B, 5, dev), "unit": "steps/s", "kind": "port",
+                    "what": "the oracle port as eager PyTorch on this GPU (fp32, TF32 off, %d clips, WavEncoder "
+                            "recomputed per pass like the reference): reference-style code on a B200, for scale" % B}
+            except Exception as e:      # a reported extra, never a reason to lose the bench line
+                line["gpu_eager_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
