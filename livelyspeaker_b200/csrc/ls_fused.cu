@@ -95,7 +95,15 @@ constexpr uint32_t WBLK_BLK = 10 * 1024;        // token-mix weights: 80 rows x 
 constexpr int ACC_COLS = 152;
 constexpr int NACC = 3;                         // head M-tiles at most
 constexpr int CAT_HI = 72;                      // first column of the hi-image product in a buffer
-constexpr int TOK_BASE = 2 * ACC_COLS;          // token-mix accumulators: TOK_BASE + (m & 1) * NROW
+// Token mix (TS mode): the LayerNorm-1 output goes from the epilogue threads straight into tensor memory as the
+// K-major A operand (hi image 40 columns = 80 rows packed in pairs, lo image 40 columns): two alternating operand
+// buffers and two alternating N=80 accumulators.  The accumulators alias channel buffer 1 (a token-mix MMA is
+// issued only after all 16 warps have published its operand, i.e. finished reading the previous channel mix; the
+// channel mix reaches buffer 1 only after every token-mix accumulator was read), the operand buffers alias
+// nothing that another warp still reads.  Channel buffer 0 stays free for the early start of the channel mix.
+constexpr int TOK_D0 = ACC_COLS;                // accumulators:    TOK_D0 + (m & 1) * 80
+constexpr int TOK_A0 = ACC_COLS + 2 * NROW;     // operand buffers: TOK_A0 + (m & 1) * 80  (hi [0,40), lo [40,80))
+constexpr int TOK_AIMG = 40;
 constexpr int KMAX = LS_MAX_FUSED_STEPS;
 
 // shared memory map (offsets from a 1024-aligned base)
@@ -115,7 +123,7 @@ constexpr uint32_t OFF_TMEM = OFF_BARS + 24 * 8;
 constexpr uint32_t SMEM_USED = OFF_TMEM + 16;
 constexpr uint32_t SMEM_DYN = SMEM_USED + 1024;         // + alignment slack
 static_assert(SMEM_DYN <= 232448, "shared memory budget");
-static_assert(NACC * ACC_COLS <= 512 && TOK_BASE + 2 * NROW <= 512, "TMEM budget");
+static_assert(NACC * ACC_COLS <= 512 && TOK_A0 + 2 * NROW <= 512, "TMEM budget");
 
 enum { BAR_FULL0 = 0, BAR_EMPTY0 = 4, BAR_UREADY0 = 8, BAR_ACC0 = 12, BAR_DRAIN0 = 16, BAR_TDRAIN0 = 18 };   // indices into the mbarrier array
 
@@ -188,9 +196,6 @@ __device__ __forceinline__ void store_split2(uint32_t u_s, uint32_t off0, uint32
   }
 }
 
-__device__ __forceinline__ uint32_t row_off(uint32_t pre_off, int n) {
-  return (pre_off ^ ((uint32_t)(n & 7) << 4)) + (uint32_t)(n & 7) * 128u + (uint32_t)(n >> 3) * 1024u;
-}
 
 // ---- epilogue thread mapping ---------------------------------------------------------------------
 // Thread (lq = warp & 3, rq = warp >> 2, lane) owns TMEM lane 32*lq + lane of EVERY M-tile, i.e. the four
@@ -339,36 +344,43 @@ __device__ __forceinline__ void store_rows(const float* hm, const float2* st, ui
   }
 }
 
-// LayerNorm 1: (h - mean) * rstd * alpha + beta for channels M0, M0 + 1 of the thread; the statistics of a row
-// are loaded once for both.  (Two channels per call: M-tiles 0-1 are published - and their token mix starts -
-// while M-tiles 2-3 are still being stored.)
-template <bool PRECISE, int M0>
-__device__ __forceinline__ void store_rows_ln1(const float (&h)[72], const float2* st, float2 ab0, float2 ab1, uint32_t u_s,
-                                               const RowBases& rb, bool odd, bool ok_tail) {
+// LayerNorm 1 of one channel's 18 rows -> the token mix's A operand in tensor memory (this thread's lane, columns
+// 9*rq .. 9*rq+8 of the hi and lo images: rows 2j, 2j+1 packed into column j).  The last row quarter also owns the
+// tail of the K range: with a spare row (TED) row 70 is the ones row that carries the bias through the GEMM and
+// row 71 is zero; rows 72..79 (columns 36..39) are zero - rewritten every time (the head's third accumulator
+// buffer overlaps these columns).
+template <bool PRECISE, bool ONES_ROW>
+__device__ __forceinline__ void store_a_tok(const float* hm, const float2* st, float2 ab, uint32_t taddr_hi, int rq,
+                                            bool ok_tail) {
+  uint32_t hi[9], lo[9];
 #pragma unroll
-  for (int j = 0; j < 16; j += 2) {
-    if ((j & 4) != 0) continue;
-    const float4 sa = *reinterpret_cast<const float4*>(st + j), sb = *reinterpret_cast<const float4*>(st + j + 4);
-#pragma unroll
-    for (int m = M0; m < M0 + 2; ++m) {
-      const float2 ab = (m == M0) ? ab0 : ab1;
-      const float* hm = h + m * NQ;
-      const uint32_t base = u_s + (uint32_t)(2 * m) * CBS;
-      store_pair<PRECISE>(base + row_addr(rb.ya0, rb.ya2, j), odd, fmaf(fmaf(hm[j], sa.x, sa.y), ab.x, ab.y),
-                          fmaf(fmaf(hm[j + 4], sb.x, sb.y), ab.x, ab.y));
-      store_pair<PRECISE>(base + row_addr(rb.ya0, rb.ya2, j + 1), odd, fmaf(fmaf(hm[j + 1], sa.z, sa.w), ab.x, ab.y),
-                          fmaf(fmaf(hm[j + 5], sb.z, sb.w), ab.x, ab.y));
+  for (int j = 0; j < NQ; j += 2) {
+    const float4 s4 = *reinterpret_cast<const float4*>(st + j);        // (rstd, -mean*rstd) of rows j, j+1
+    const float u0 = fmaf(fmaf(hm[j], s4.x, s4.y), ab.x, ab.y), u1 = fmaf(fmaf(hm[j + 1], s4.z, s4.w), ab.x, ab.y);
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(u0, u1);           // low half = row j (k even)
+    const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
+    hi[j >> 1] = hb;
+    if (PRECISE) {
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(u0 - __uint_as_float(hb << 16), u1 - __uint_as_float(hb & 0xFFFF0000u));
+      lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
     }
   }
-  if (ok_tail) {
-    const float4 sa = *reinterpret_cast<const float4*>(st + 16);
-#pragma unroll
-    for (int m = M0; m < M0 + 2; ++m) {
-      const float2 ab = (m == M0) ? ab0 : ab1;
-      store_pair<PRECISE>(u_s + (uint32_t)(2 * m) * CBS + rb.ytail, odd, fmaf(fmaf(h[m * NQ + 16], sa.x, sa.y), ab.x, ab.y),
-                          fmaf(fmaf(h[m * NQ + 17], sa.z, sa.w), ab.x, ab.y));
-    }
+  if (!ok_tail) {                       // rows 16, 17 of this quarter do not exist: (1.0, 0) or zeros
+    hi[8] = ONES_ROW ? 0x00003F80u : 0u;
+    lo[8] = 0u;
   }
+  const uint32_t t_hi = taddr_hi + 9u * (uint32_t)rq;
+  tmem_st8(t_hi, hi);
+  tmem_st1(t_hi + 8, hi[8]);
+  if (PRECISE) {
+    tmem_st8(t_hi + TOK_AIMG, lo);
+    tmem_st1(t_hi + TOK_AIMG + 8, lo[8]);
+  }
+  if (rq == 3) {                        // warp-uniform
+    tmem_st4(taddr_hi + 36, 0u, 0u, 0u, 0u);
+    if (PRECISE) tmem_st4(taddr_hi + TOK_AIMG + 36, 0u, 0u, 0u, 0u);
+  }
+  tmem_st_wait();
 }
 
 // This thread's 18 columns [taddr, taddr + 18) of one accumulator (CAT: plus the columns 72 further that hold
@@ -534,13 +546,11 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
     {   // all 32 lanes run this role in lock step; one elected lane issues (see ls_tc.cuh)
       uint32_t it = 0, uphase = 0, dphase = 0, tphase = 0;
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);    // provably warp-uniform copy
-      constexpr uint32_t id_cat = idesc_bf16(128, NCAT, 0, 0), id_kk = idesc_bf16(128, NROW, 0, 0),
-                         id_mk = idesc_bf16(128, NROW, 1, 0);
+      constexpr uint32_t id_cat = idesc_bf16(128, NCAT, 0, 0), id_kk = idesc_bf16(128, NROW, 0, 0);
       // Descriptor words: high word constant per layout, low word = (addr >> 4) | LBO field.
       constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
       const uint32_t u_s = smem_u32(sm + OFF_U);
       const uint32_t uk = desc_lo32(u_s, 16);          // K-major view of block 0 from its lo image
-      const uint32_t um = desc_lo32(u_s, CBS);         // MN-major view of the lo image
       constexpr uint32_t HI = HI_OFF >> 4;             // descriptor-address distance lo image -> hi image
       constexpr uint32_t BLK = CBS >> 4;               // ... between 64-channel blocks
 #if LS_MMA_PROF
@@ -640,17 +650,17 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
 #pragma unroll 1
           for (uint32_t mt = 0; mt < 4; ++mt) {
             LS_PROF(prof_u, mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + mt), uphase & 1);)
-            if (mt >= 2) mbar_wait_s(bars_s + 8 * (BAR_TDRAIN0 + mt - 2), tphase & 1);   // token buffer mt - 2 read
+            if (mt >= 2) mbar_wait_s(bars_s + 8 * (BAR_TDRAIN0 + mt - 2), tphase & 1);   // token accumulator mt - 2 read
             tc_fence_after_sync();
-            const uint32_t d = tmem_u + (uint32_t)TOK_BASE + (mt & 1) * NROW;
-            const uint32_t ua = um + 2 * mt * BLK;         // lo image of this M-tile's channels, MN-major
+            const uint32_t d = tmem_u + (uint32_t)TOK_D0 + (mt & 1) * NROW;
+            const uint32_t a_hi = tmem_u + (uint32_t)TOK_A0 + (mt & 1) * NROW, a_lo = a_hi + TOK_AIMG;
 #pragma unroll
             for (uint32_t ks = 0; ks < 5; ++ks) {
-              const uint32_t bw = wl[ks >> 2] + 2 * (ks & 3), ao = ua + ks * (2048 >> 4);
-              umma_bf16_split_elect(d, ao + HI, DH, bw, DH, id_mk, ks == 0 ? 0u : 1u);
+              const uint32_t bw = wl[ks >> 2] + 2 * (ks & 3);
+              umma_bf16_ts_elect(d, a_hi + 8 * ks, bw, DH, id_kk, ks == 0 ? 0u : 1u);
               if (PRECISE) {
-                umma_bf16_split_elect(d, ao, DH, bw, DH, id_mk, 1u);
-                umma_bf16_split_elect(d, ao + HI, DH, wl[NW - 2 + (ks >> 2)] + 2 * (ks & 3), DH, id_mk, 1u);
+                umma_bf16_ts_elect(d, a_lo + 8 * ks, bw, DH, id_kk, 1u);
+                umma_bf16_ts_elect(d, a_hi + 8 * ks, wl[NW - 2 + (ks >> 2)] + 2 * (ks & 3), DH, id_kk, 1u);
               }
             }
             umma_commit_s_elect(bars_s + 8 * (BAR_ACC0 + mt));
@@ -816,19 +826,26 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         if (l == 0) ln_stats_q<0>(h, sm, rq, false);     // provisional means for the shift
         ln_stats_q<0>(h, sm, rq, true);
         stamp();   // LN1 stats done
-        store_rows_ln1<PRECISE, 0>(h, stats_q, pab_s[c0], pab_s[c0 + 128], u_s, rb, odd, ok_tail);
-        publish_u(0);
-        publish_u(1);
-        store_rows_ln1<PRECISE, 2>(h, stats_q, pab_s[c0 + 256], pab_s[c0 + 384], u_s, rb, odd, ok_tail);
-        publish_u(2);
-        publish_u(3);
-        stamp();   // U1 published
+        auto publish_a = [&](int m) {   // this warp's part of the token-mix operand of M-tile m is in tensor memory
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[BAR_UREADY0 + m]);
+        };
+        auto a_tok = [&](int m) {
+          store_a_tok<PRECISE, TokBias<S>::kInGemm>(h + m * NQ, stats_q, pab_s[c0 + 128 * m],
+                                                    lane_base + (uint32_t)(TOK_A0 + (m & 1) * NROW), rq, ok_tail);
+          publish_a(m);
+        };
+        a_tok(0);
+        a_tok(1);
+        stamp();   // U1 published (M-tiles 0, 1)
         // token mix epilogue x = x + silu(conv + bias), then straight into the channel-mix operand:
         // normalised with the LN1 statistics; the exact LN2 statistics follow while the GEMM runs
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          wait_acc(m);
-          acc_rows_tok(lane_base + (uint32_t)(TOK_BASE + (m & 1) * NROW + r0), [&](int j, float v) {
+          wait_acc(m);                  // accumulator m complete => operand buffer m & 1 is free again
+          if (m + 2 < 4) a_tok(m + 2);
+          acc_rows_tok(lane_base + (uint32_t)(TOK_D0 + (m & 1) * NROW + r0), [&](int j, float v) {
             if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[r0 + j]);
           });
           if (m < 2) drained(BAR_TDRAIN0 + m);
