@@ -16,10 +16,10 @@
 //   * each of the 512 epilogue threads keeps 4 channels x 18 rows of the fp32 residual stream
 //     in REGISTERS for the whole 8-layer stack;
 //   * TMEM holds only accumulators;
-//   * shared memory holds the bf16 operand tile U (LayerNorm output) - the very same bytes serve as
-//     the K-major B operand of the channel-mix GEMM and as the MN-major A operand of the token-mix
-//     GEMM (ls_tc.cuh, validated by umma_probe.cu) - plus a 4-slot ring of weight stages streamed
-//     from L2 by 1-D bulk async copies.
+//   * shared memory holds the bf16 operand tile U of the channel-type GEMMs (input projection, channel mix,
+//     head) as their K-major B operand, plus a 4-slot ring of weight stages streamed from L2 by 1-D bulk async
+//     copies; the token mix takes its A operand (LayerNorm 1's output) from TENSOR MEMORY, written there by the
+//     epilogue threads (TS mode).
 // Precision: PRECISE = bf16x3 (hi*hi + hi*lo + lo*hi, fp32 accumulate) meets the rtol 1e-3 /
 // atol 1e-4 parity bar; !PRECISE = plain bf16 operands (fast mode).
 //
@@ -436,9 +436,9 @@ __device__ __forceinline__ void for_acc_cat(uint32_t taddr, F&& f) {
   }
 }
 
-// Token-mix bias through the GEMM: when the 72-row tile has a spare row (TED: 2S = 70), that row of
-// U holds 1.0 and column 2S of the block-diagonal weight holds the bias, so the epilogue needs no
-// per-row bias load.  BEAT (2S = 72) has no spare row and adds the bias from shared memory.
+// Token-mix bias through the GEMM: when the 72-row tile has a spare row (TED: 2S = 70), that row of the
+// token-mix operand holds 1.0 (store_a_tok) and column 2S of the block-diagonal weight holds the bias, so the
+// epilogue needs no per-row bias load.  BEAT (2S = 72) has no spare row and adds the bias from shared memory.
 template <int S>
 struct TokBias { static constexpr bool kInGemm = (2 * S + 1 <= 72); };
 
@@ -474,8 +474,6 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
   }
   if (warp == 17) tmem_alloc<512>(tmem_slot);
   __syncthreads();
-  if (TokBias<S>::kInGemm && tid < LS_D)          // the ones row (hi = 1.0, lo = 0) - never overwritten
-    sts_u16(smem_u32(sm + OFF_U) + HI_OFF + tile_off(R, tid, CBS), (uint16_t)0x3F80u);
   fence_proxy_async_smem();
   tc_fence_before_sync();
 #if LS_MULTICAST
