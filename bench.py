@@ -57,47 +57,100 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line), read through NVML
+    from a thread of this process (two light queries every 50 ms).  Spawning / polling `nvidia-smi` instead
+    measurably stalls the launching thread of a 150 ms timed region (one run: 878 instead of ~1400 steps/s); it
+    remains the fallback when pynvml is missing.  Started before the warm-up, marked around the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx = [], None, gpu_index      # rows: (t, sm_mhz, max_mhz, [reason names])
+        self.t0 = self.t1 = None
+        self.nvml, self.stop_flag, self.how = None, False, None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        return self.idx
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown),
+                    ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                    ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap)]
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.rows.append((time.perf_counter(), float(sm), float(mx), [n for n, b in bits if r & b]))
+                    except Exception:
+                        pass
+                    time.sleep(0.05)
+
+            self.nvml, self.how = pynvml, "nvml"
+            threading.Thread(target=loop, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            self.how = "nvidia-smi"
+            threading.Thread(target=self._read_smi, daemon=True).start()
         except OSError:
             self.proc = None
 
-    def _read(self):
+    def _read_smi(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]),
+                                  [n for n, v in zip(self.NAMES, r[5:9]) if v.lower().startswith("active")]))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+
+    def wait_first_sample(self, timeout=5.0):
+        t = time.perf_counter()
+        while self.how is not None and not self.rows and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if self.t0 is not None and self.t0 - 0.06 <= r[0] <= (self.t1 or r[0]) + 0.12]
+        window = "timed region"
+        if not rows:
+            rows, window = list(self.rows), "whole run (no sample fell into the timed region)"
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
+                "reasons": reasons, "samples": len(rows), "window": window, "via": self.how}
 
 
 def cpu_port_steps_per_s(dims, batch_equiv, n_steps, warmup, sample_batch, threads):
@@ -283,21 +336,28 @@ def main():
     def chunks(k0, n):
         return [(k0 + i, min(C, n - i)) for i in range(0, n, C)]
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for k0, n in chunks(0, W):
         x = run_chunk(k0, n, x)
     sync_all()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.wait_first_sample()
     launches0 = eng.launch_count()
     timed = chunks(W, K)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in timed]
+    import gc
+    gc.collect()
+    gc.disable()                               # no collector pause on the launching thread inside the timed region
     sync_all()
+    clocks.mark_begin()
     for j, (k0, n) in enumerate(timed):
         flush_buf.zero_()                      # evict L2 (126 MB) - outside the event bracket
         ev[j][0].record()
         x = run_chunk(k0, n, x)
         ev[j][1].record()
     sync_all()
+    clocks.mark_end()
+    gc.enable()
     launches = eng.launch_count() - launches0
     clk = clocks.stop()
     t_ms = sum(s.elapsed_time(e) for s, e in ev)
