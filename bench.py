@@ -278,6 +278,7 @@ def main():
     import torch.distributed as dist
     import livelyspeaker_b200 as ls
     from livelyspeaker_b200 import beat_model_util, sharding
+    from livelyspeaker_b200 import gaussian_diffusion as gd
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback exists)"
     torch.cuda.set_device(local_rank)
@@ -322,10 +323,15 @@ def main():
 
     def run_chunk(k0, n, x_in):
         """n consecutive loop iterations as p_sample_loop runs them on the fused route: the reference's
-        per-step draws (3 torch RNG launches per step), then ONE ls_step_multi launch."""
-        e_c = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]
-        e_u = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]
-        nz = [torch.randn_like(perm_like) for _ in range(n)]
+        per-step draws (3 torch RNG kernels per step, replayed from a CUDA graph for full chunks), then ONE
+        ls_step_multi launch."""
+        if n == C and n > 1 and k0 > 0 and diffusion.graph_draws:
+            # like p_sample_loop: full chunks after the first replay their 3n draws from a CUDA graph
+            e_c, e_u, nz = eng.graphed_draws(n, B, 512, perm_like, gd._GraphedDraws).draw()
+        else:
+            e_c = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]
+            e_u = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]
+            nz = [torch.randn_like(perm_like) for _ in range(n)]
         xs = torch.empty((n,) + tuple(x_in.shape), device=dev)
         if n == 1:
             eng.step(params[k0], x_in, e_c[0], e_u[0], nz[0], scale, xs[0], None)

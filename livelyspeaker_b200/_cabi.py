@@ -289,6 +289,14 @@ class Engine:
             sb, sj, sd, sf = noise.stride()
         return noise, noise.data_ptr(), sb, sd, sf
 
+    def graphed_draws(self, K, B, d, perm_like, factory):
+        """Per-engine cache of the CUDA-graph-captured draws of a chunk (gaussian_diffusion._GraphedDraws)."""
+        key = (K, B, d, tuple(perm_like.shape), tuple(perm_like.stride()))
+        cache = self.__dict__.setdefault("_graphed", {})
+        if key not in cache:
+            cache[key] = factory(K, B, d, perm_like)
+        return cache[key]
+
     def step_multi(self, params, x_t, eps_c, eps_u, noise, scale, x_prev, pred_x0):
         """len(params) <= MAX_FUSED_STEPS consecutive steps in one launch (ls_step_multi).
         eps_c / eps_u / noise: per-step lists; x_prev / pred_x0: dense [K,B,J,D,F] outputs

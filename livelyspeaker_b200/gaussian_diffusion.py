@@ -98,6 +98,40 @@ class ReplayNoise:
         return self._next(like.shape, like.device)
 
 
+class _GraphedDraws:
+    """The 3*K torch draws of one fused chunk (cond style, uncond style, step noise - per step, the reference's
+    order) captured once in a CUDA graph and replayed per chunk: same generator, same Philox offsets, hence the
+    same numbers as the eager calls (torch's graph-safe RNG), without 3*K launch gaps per chunk.  Buffers are
+    static; a replay overwrites them only after the previous chunk's kernel (same stream)."""
+
+    def __init__(self, K, B, d, perm_like):
+        dev = perm_like.device
+        self.K = K
+        self.eps_c = [th.empty(B, 1, d, device=dev) for _ in range(K)]
+        self.eps_u = [th.empty(B, 1, d, device=dev) for _ in range(K)]
+        self.nz = [th.empty_like(perm_like) for _ in range(K)]          # keeps the [F,B,J,D] memory order
+        state = th.cuda.get_rng_state(dev)                               # warm-up and capture must not consume draws
+        side = th.cuda.Stream(device=dev)
+        side.wait_stream(th.cuda.current_stream(dev))
+        with th.cuda.stream(side):
+            self._fill()
+        th.cuda.current_stream(dev).wait_stream(side)
+        self.graph = th.cuda.CUDAGraph()
+        with th.cuda.graph(self.graph):
+            self._fill()
+        th.cuda.set_rng_state(state, dev)
+
+    def _fill(self):
+        for k in range(self.K):
+            self.eps_c[k].normal_()
+            self.eps_u[k].normal_()
+            self.nz[k].normal_()
+
+    def draw(self):
+        self.graph.replay()
+        return self.eps_c, self.eps_u, self.nz
+
+
 def _extract_into_tensor(arr, timesteps, broadcast_shape):
     """fp64 table -> fp32 values gathered at `timesteps`, broadcast to `broadcast_shape`."""
     res = th.from_numpy(arr).to(device=timesteps.device)[timesteps].float()
@@ -110,6 +144,8 @@ class GaussianDiffusion:
     # Loop iterations per launch on the fused route of the non-progressive loops (ls_step_multi);
     # 1 = one launch per step.  The *_progressive generators always run step by step.
     fused_chunk = MAX_FUSED_STEPS
+    # Replay the draws of a full chunk from a CUDA graph (see _GraphedDraws); only with the default torch noise.
+    graph_draws = True
 
     def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False,
                  lambda_rcxyz=0., lambda_vel=0., lambda_pose=1., lambda_orient=1., lambda_loc=1.,
@@ -390,17 +426,24 @@ class GaussianDiffusion:
                 else:
                     indices = tqdm(indices)
             k = 0
+            graphed = None
             while chunk > 1 and k < len(indices):
                 # `chunk` loop iterations per launch (ls_step_multi).  The draws keep the reference's order
                 # (cond style, uncond style, step noise - per step), they are only made ahead of the launch.
                 idx = indices[k:k + chunk]
                 K = len(idx)
-                eps_c, eps_u, nzs = [], [], []
-                for j in range(K):
-                    eps_c.append(src.randn((B, 1, rag.latent_dim), dev))
-                    eps_u.append(src.randn((B, 1, rag.latent_dim), dev))
-                    nz = src.randn_like(like if k + j == 0 else perm_like)
-                    nzs.append(nz[[0]].expand(B, -1, -1, -1) if const_noise else nz)
+                # full chunks after the first one (whose step-0 noise has x_T's own layout) replay a captured graph
+                if k > 0 and K == chunk and self.graph_draws and type(src) is TorchNoise and not const_noise:
+                    if graphed is None:
+                        graphed = eng.graphed_draws(K, B, rag.latent_dim, perm_like, _GraphedDraws)
+                    eps_c, eps_u, nzs = graphed.draw()
+                else:
+                    eps_c, eps_u, nzs = [], [], []
+                    for j in range(K):
+                        eps_c.append(src.randn((B, 1, rag.latent_dim), dev))
+                        eps_u.append(src.randn((B, 1, rag.latent_dim), dev))
+                        nz = src.randn_like(like if k + j == 0 else perm_like)
+                        nzs.append(nz[[0]].expand(B, -1, -1, -1) if const_noise else nz)
                 xs = th.empty((K,) + tuple(x_cur.shape), device=dev)
                 x0s = th.empty_like(xs)
                 eng.step_multi([self.step_params(i, ddim=ddim, eta=eta, clip_denoised=clip_denoised) for i in idx],

@@ -271,6 +271,22 @@ def test_same_seed_rng_order_and_layout_on_device():
     _close(got, want)
 
 
+def test_graphed_draws_equal_eager_draws():
+    """Chunks after the first replay their 48 torch draws from a CUDA graph: same generator, same Philox offsets,
+    so the samples must be bit-identical to the loop that makes the draws eagerly - and to the step-by-step loop."""
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    y = synthetic.synth_cond(dims, 5, device=DEV)
+    outs = []
+    for graph, chunk in ((True, 16), (False, 16), (True, 16), (False, 1)):
+        diffusion.graph_draws, diffusion.fused_chunk = graph, chunk
+        torch.manual_seed(99)
+        outs.append(diffusion.p_sample_loop(cfg, (5, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=30))
+        tail = torch.randn(4, device=DEV)          # the generator must end up in the same state, too
+        outs.append(tail)
+    for i in range(2, len(outs), 2):
+        assert torch.equal(outs[0], outs[i]) and torch.equal(outs[1], outs[i + 1]), "variant %d differs" % (i // 2)
+
+
 def test_progressive_generator_and_dump_steps():
     dims, sd, cfg, diffusion = build("ted", "ddim100")
     y = synthetic.synth_cond(dims, 2, device=DEV)
