@@ -178,25 +178,6 @@ __device__ __forceinline__ void store_split(uint32_t u_s, uint32_t off, float v)
   }
 }
 
-// Two values (rows n0, n1 of this thread's channel) -> bf16 hi (+ lo) with the packed converter
-// (F2FP, full-rate pipe; the scalar F2F conversion issues at MUFU rate and was the LayerNorm
-// store bottleneck).
-template <bool PRECISE>
-__device__ __forceinline__ void store_split2(uint32_t u_s, uint32_t off0, uint32_t off1, float v0, float v1) {
-  const __nv_bfloat162 hi = __floats2bfloat162_rn(v0, v1);      // .x = v0 (low half), .y = v1 (high half)
-  const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi);
-  sts_u16(u_s + HI_OFF + off0, (uint16_t)(hb & 0xFFFFu));
-  sts_u16(u_s + HI_OFF + off1, (uint16_t)(hb >> 16));
-  if (PRECISE) {
-    const float r0 = v0 - __uint_as_float(hb << 16), r1 = v1 - __uint_as_float(hb & 0xFFFF0000u);
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(r0, r1);
-    const uint32_t lb = *reinterpret_cast<const uint32_t*>(&lo);
-    sts_u16(u_s + off0, (uint16_t)(lb & 0xFFFFu));
-    sts_u16(u_s + off1, (uint16_t)(lb >> 16));
-  }
-}
-
-
 // ---- epilogue thread mapping ---------------------------------------------------------------------
 // Thread (lq = warp & 3, rq = warp >> 2, lane) owns TMEM lane 32*lq + lane of EVERY M-tile, i.e. the four
 // channels c_m = 128*m + 32*lq + lane, and the NQ = 18 tile rows [18*rq, 18*rq + 18).  So
@@ -560,8 +541,10 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
 #endif
       auto wait_u_all = [&]() {       // whole operand tile published (K = all channels)
         LS_PROF(prof_u, {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + m), uphase & 1);
+          mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + 0), uphase & 1);
+          mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + 1), uphase & 1);
+          mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + 2), uphase & 1);
+          mbar_wait_s(bars_s + 8 * (BAR_UREADY0 + 3), uphase & 1);
         })
         ++uphase;
         tc_fence_after_sync();
