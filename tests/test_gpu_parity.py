@@ -401,6 +401,41 @@ def test_multi_step_launch_equals_single_steps(impl, B, K):
     assert torch.isfinite(xs).all()
 
 
+def test_beat_full_size_b256_multi_step_properties():
+    """BASELINE config 4 shape (BEAT, B=256, J*D=282, S=36: no spare tile row, 3 head M-tiles): a 3-step launch is
+    deterministic, equals single steps bit for bit, and clip b of the big batch equals the same clip in a batch of 3."""
+    dims, sd, cfg, diffusion = build("beat", "")
+    B, K = 256, 3
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    eng = cfg.model.engine(B)
+    eng.set_cond(y, force=True)
+    g = torch.Generator().manual_seed(12)
+    shape = (B, dims.njoints, dims.nfeats, 34)
+    x = torch.randn(*shape, generator=g).to(DEV)
+    e_c = [torch.randn(B, 1, 512, generator=g).to(DEV) for _ in range(K)]
+    e_u = [torch.randn(B, 1, 512, generator=g).to(DEV) for _ in range(K)]
+    nz = [torch.randn(*shape, generator=g).to(DEV) for _ in range(K)]
+    params = [diffusion.step_params(i, ddim=False, clip_denoised=False) for i in (700, 699, 698)]
+    xs, xs2 = torch.empty(K, *shape, device=DEV), torch.empty(K, *shape, device=DEV)
+    eng.step_multi(params, x, e_c, e_u, nz, y["scale"], xs, None)
+    eng.step_multi(params, x, e_c, e_u, nz, y["scale"], xs2, None)
+    assert torch.equal(xs, xs2) and torch.isfinite(xs).all()
+    cur = x
+    for k in range(K):
+        nxt = torch.empty_like(x)
+        eng.step(params[k], cur, e_c[k], e_u[k], nz[k], y["scale"], nxt, None)
+        assert torch.equal(nxt, xs[k])
+        cur = nxt
+    idx = torch.tensor([0, 100, 255], device=DEV)
+    ys = {k: (v[idx].clone() if torch.is_tensor(v) else v) for k, v in y.items()}
+    eng3 = cfg.model.engine(3)
+    eng3.set_cond(ys, force=True)
+    out3 = torch.empty(3, dims.njoints, dims.nfeats, 34, device=DEV)
+    eng3.step(params[0], x[idx].contiguous(), e_c[0][idx].contiguous(), e_u[0][idx].contiguous(), nz[0][idx].contiguous(),
+              ys["scale"], out3, None)
+    _close(out3, xs[0][idx], rtol=1e-5, atol=1e-5)
+
+
 def test_error_paths():
     from livelyspeaker_b200._cabi import LsError
     dims, sd, cfg, diffusion = build("ted", "ddim100")
