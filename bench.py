@@ -329,9 +329,15 @@ def main():
         """n consecutive loop iterations as p_sample_loop runs them on the fused route: the reference's
         per-step draws (3 torch RNG kernels per step, replayed from a CUDA graph for full chunks), then ONE
         ls_step_multi launch."""
+        graphed = None
         if n == C and n > 1 and k0 > 0 and diffusion.graph_draws:
             # like p_sample_loop: full chunks after the first replay their 3n draws from a CUDA graph
-            e_c, e_u, nz = eng.graphed_draws(n, B, 512, perm_like, gd._GraphedDraws).draw()
+            try:
+                graphed = eng.graphed_draws(n, B, 512, perm_like, gd._GraphedDraws)
+            except RuntimeError:
+                diffusion.graph_draws = False
+        if graphed is not None:
+            e_c, e_u, nz = graphed.draw()
         else:
             e_c = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]
             e_u = [torch.randn(B, 1, 512, device=dev) for _ in range(n)]

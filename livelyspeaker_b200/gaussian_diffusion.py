@@ -433,9 +433,13 @@ class GaussianDiffusion:
                 idx = indices[k:k + chunk]
                 K = len(idx)
                 # full chunks after the first one (whose step-0 noise has x_T's own layout) replay a captured graph
-                if k > 0 and K == chunk and self.graph_draws and type(src) is TorchNoise and not const_noise:
-                    if graphed is None:
+                if k > 0 and K == chunk and self.graph_draws and type(src) is TorchNoise and not const_noise \
+                        and graphed is None:
+                    try:
                         graphed = eng.graphed_draws(K, B, rag.latent_dim, perm_like, _GraphedDraws)
+                    except RuntimeError:          # capture not possible here (e.g. already capturing): eager draws
+                        self.graph_draws = False
+                if graphed is not None and k > 0 and K == chunk:
                     eps_c, eps_u, nzs = graphed.draw()
                 else:
                     eps_c, eps_u, nzs = [], [], []
