@@ -327,14 +327,14 @@ def main():
 
     def run_chunk(k0, n, x_in):
         """n consecutive loop iterations as p_sample_loop runs them on the fused route: the reference's
-        per-step draws (3 torch RNG kernels per step, replayed from a CUDA graph for full chunks), then ONE
+        per-step draws (for full chunks after the first: one torch-compatible launch, or a CUDA-graph replay of the
+        3n torch kernels when that kernel does not verify against torch), then ONE
         ls_step_multi launch."""
         graphed = None
         if n == C and n > 1 and k0 > 0 and diffusion.graph_draws:
             # like p_sample_loop: full chunks after the first replay their 3n draws from a CUDA graph
-            try:
-                graphed = eng.graphed_draws(n, B, 512, perm_like, gd._GraphedDraws)
-            except RuntimeError:
+            graphed = gd.chunk_draws(eng, n, B, 512, perm_like)
+            if graphed is None:
                 diffusion.graph_draws = False
         if graphed is not None:
             e_c, e_u, nz = graphed.draw()

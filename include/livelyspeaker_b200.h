@@ -214,6 +214,17 @@ typedef struct ls_sag_weights {
 int ls_sag_decode(const ls_sag_weights* w, int32_t B, const float* x, const float* z,
                   const uint8_t* mask, float* out, void* stream);
 
+/* The n torch.randn / randn_like draws of a fused chunk in one launch: tensor i (dense, fp32,
+ * numels[i] elements, written in memory order) receives exactly the values torch's CUDA
+ * generator with `seed` would produce for it at Philox offset `philox_offset` + the increments
+ * of tensors 0..i-1 (ATen/native/cuda/DistributionTemplates.h).  *total_increment is what the
+ * caller must add to the generator's offset afterwards.  outs / numels are HOST arrays.  The
+ * Python layer verifies the equality against torch once per process before using it.        */
+#define LS_RANDN_MAX_TENSORS 48
+int ls_randn_torch_compat(int32_t n, float* const* outs, const int64_t* numels, uint64_t seed,
+                          uint64_t philox_offset, uint64_t* total_increment, int32_t device,
+                          void* stream);
+
 /* Introspection used by tests / bench: number of kernels launched by this handle
  * since creation, and read-back of the step-invariant buffers.                    */
 int64_t ls_launch_count(const ls_handle* h);

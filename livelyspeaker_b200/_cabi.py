@@ -19,7 +19,7 @@ IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
-           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_q_sample", "ls_launch_count",
+           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
            "ls_debug_buffer"]
 
 
@@ -80,6 +80,8 @@ def load_library():
                             c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.ls_step_multi.argtypes = [c_void_p, c_int32, c_int32, POINTER(LsStepParams), POINTER(LsStepIO), c_void_p,
                                   c_void_p, c_void_p]
+    lib.ls_randn_torch_compat.argtypes = [c_int32, POINTER(c_void_p), POINTER(c_int64), ctypes.c_uint64, ctypes.c_uint64,
+                                          POINTER(ctypes.c_uint64), c_int32, c_void_p]
     lib.ls_q_sample.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p]
     lib.ls_launch_count.argtypes = [c_void_p]
     lib.ls_launch_count.restype = c_int64
@@ -291,7 +293,7 @@ class Engine:
 
     def graphed_draws(self, K, B, d, perm_like, factory):
         """Per-engine cache of the CUDA-graph-captured draws of a chunk (gaussian_diffusion._GraphedDraws)."""
-        key = (K, B, d, tuple(perm_like.shape), tuple(perm_like.stride()))
+        key = (factory.__name__, K, B, d, tuple(perm_like.shape), tuple(perm_like.stride()))
         cache = self.__dict__.setdefault("_graphed", {})
         if key not in cache:
             cache[key] = factory(K, B, d, perm_like)

@@ -1,0 +1,79 @@
+// torch.randn-compatible normal draws for many tensors in ONE launch.
+//
+// The reference draws three tensors per denoising step with torch.randn / randn_like (gaussian_diffusion.py:543,
+// RAG.py:10-13); a fused chunk of 16 steps therefore needs 48 tiny torch kernels.  This kernel reproduces, tensor
+// by tensor, exactly what ATen's CUDA normal_ does (ATen/native/cuda/DistributionTemplates.h:
+// calc_execution_policy + distribution_elementwise_grid_stride_kernel + curand_normal4): Philox4x32-10 seeded with
+// the generator's seed, subsequence = global thread index of a 256-thread grid of
+// min(#SM * (maxThreadsPerSM / 256), ceil(numel / 256)) blocks, offset = the generator's Philox offset, which every
+// tensor advances by ((numel - 1) / (256 * grid * 4) + 1) * 4.  Element li of a dense tensor is written at memory
+// offset li (TensorIterator walks dense tensors in memory order, also permuted ones).  The Python side checks the
+// result bit for bit against torch before it trusts it (livelyspeaker_b200/gaussian_diffusion.py::_FusedDraws) and
+// moves the generator's offset by the total increment, so the draw stream stays the reference's.
+#include <curand_kernel.h>
+
+#include "ls_internal.cuh"
+
+namespace {
+
+constexpr int RN_BLOCK = 256, RN_UNROLL = 4, RN_MAX = LS_RANDN_MAX_TENSORS;
+
+struct RandnJob {
+  float* out;
+  unsigned long long offset;
+  unsigned int numel, grid;
+};
+struct RandnJobs {
+  RandnJob j[RN_MAX];
+};
+
+__global__ void __launch_bounds__(RN_BLOCK) randn_torch_compat_kernel(const __grid_constant__ RandnJobs jobs,
+                                                                      unsigned long long seed) {
+  const RandnJob& jb = jobs.j[blockIdx.y];
+  if (blockIdx.x >= jb.grid) return;
+  const long long idx = (long long)blockIdx.x * RN_BLOCK + threadIdx.x;
+  curandStatePhilox4_32_10_t state;
+  curand_init(seed, idx, jb.offset, &state);
+  const long long stride = (long long)RN_BLOCK * jb.grid, numel = jb.numel;
+  const long long rounded = ((numel - 1) / (stride * RN_UNROLL) + 1) * stride * RN_UNROLL;
+  for (long long li = idx; li < rounded; li += stride * RN_UNROLL) {
+    const float4 r = curand_normal4(&state);
+#pragma unroll
+    for (int ii = 0; ii < RN_UNROLL; ++ii) {
+      const long long l = li + stride * ii;
+      if (l < numel) jb.out[l] = (&r.x)[ii];
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ls_randn_torch_compat(int32_t n, float* const* outs, const int64_t* numels, uint64_t seed,
+                                     uint64_t philox_offset, uint64_t* total_increment, int32_t device, void* stream) {
+  if (n < 1 || n > RN_MAX || !outs || !numels || !total_increment)
+    return ls_fail(nullptr, LS_EINVAL, "ls_randn_torch_compat: 1..%d tensors", RN_MAX);
+  int sms = 0, tpsm = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&tpsm, cudaDevAttrMaxThreadsPerMultiProcessor, device) != cudaSuccess)
+    return ls_fail(nullptr, LS_ECUDA, "ls_randn_torch_compat: cannot query device %d", device);
+  const unsigned int grid_cap = (unsigned int)sms * (unsigned int)(tpsm / RN_BLOCK);
+  RandnJobs jobs{};
+  unsigned long long off = philox_offset;
+  unsigned int max_grid = 1;
+  for (int i = 0; i < n; ++i) {
+    if (!outs[i] || numels[i] < 1 || numels[i] > 0x7fffffffLL)
+      return ls_fail(nullptr, LS_EINVAL, "ls_randn_torch_compat: tensor %d", i);
+    const unsigned long long numel = (unsigned long long)numels[i];
+    unsigned int grid = (unsigned int)((numel + RN_BLOCK - 1) / RN_BLOCK);
+    if (grid > grid_cap) grid = grid_cap;
+    jobs.j[i] = RandnJob{outs[i], off, (unsigned int)numel, grid};
+    off += ((numel - 1) / ((unsigned long long)RN_BLOCK * grid * RN_UNROLL) + 1) * 4ull;
+    if (grid > max_grid) max_grid = grid;
+  }
+  for (int i = n; i < RN_MAX; ++i) jobs.j[i] = RandnJob{nullptr, 0, 0, 0};
+  randn_torch_compat_kernel<<<dim3(max_grid, n), RN_BLOCK, 0, (cudaStream_t)stream>>>(jobs, seed);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_randn_torch_compat: %s", cudaGetErrorString(e));
+  *total_increment = off - philox_offset;
+  return LS_OK;
+}

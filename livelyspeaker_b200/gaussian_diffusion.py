@@ -132,6 +132,79 @@ class _GraphedDraws:
         return self.eps_c, self.eps_u, self.nz
 
 
+def chunk_draws(eng, K, B, d, perm_like):
+    """Source of the 3*K draws of a full fused chunk: the one-launch torch-compatible kernel when it verifiably
+    reproduces torch here, else the CUDA-graph replay of the torch calls, else None (eager calls)."""
+    try:
+        fused = eng.graphed_draws(K, B, d, perm_like, _FusedDraws)
+        if fused.ok:
+            return fused
+    except Exception:
+        pass
+    try:
+        return eng.graphed_draws(K, B, d, perm_like, _GraphedDraws)
+    except RuntimeError:
+        return None
+
+
+class _FusedDraws:
+    """The same 3*K draws from ONE launch of ls_randn_torch_compat, which reproduces ATen's CUDA normal_ (Philox
+    subsequence per thread of torch's grid, curand_normal4, torch's offset increments) and then moves the
+    generator's offset like the 3*K torch calls would.  Trusted only after a bit-for-bit comparison with torch on
+    this very set of tensors (values and final generator state); `ok` is False otherwise and the caller falls back
+    to _GraphedDraws."""
+
+    def __init__(self, K, B, d, perm_like):
+        import ctypes
+        from . import _cabi
+        dev = perm_like.device
+        self.dev, self.lib, self.ct = dev, _cabi.load_library(), ctypes
+        self.eps_c = [th.empty(B, 1, d, device=dev) for _ in range(K)]
+        self.eps_u = [th.empty(B, 1, d, device=dev) for _ in range(K)]
+        self.nz = [th.empty_like(perm_like) for _ in range(K)]
+        order = [t for k in range(K) for t in (self.eps_c[k], self.eps_u[k], self.nz[k])]
+        self.n = len(order)
+        self.ptrs = (ctypes.c_void_p * self.n)(*[t.data_ptr() for t in order])
+        self.numels = (ctypes.c_int64 * self.n)(*[t.numel() for t in order])
+        self.ok = self.n <= 48 and all(self._dense(t) for t in order) and self._matches_torch(order)
+
+    @staticmethod
+    def _dense(t):
+        """Dense in memory in some dimension order (then torch's iterator walks it in memory order)."""
+        dims = sorted(range(t.dim()), key=lambda i: -t.stride(i))
+        return t.permute(dims).is_contiguous()
+
+    def _launch(self):
+        gen = th.cuda.default_generators[self.dev.index if self.dev.index is not None else th.cuda.current_device()]
+        seed, off = gen.initial_seed(), gen.get_offset()
+        inc = self.ct.c_uint64(0)
+        with th.cuda.device(self.dev):
+            rc = self.lib.ls_randn_torch_compat(self.n, self.ptrs, self.numels, self.ct.c_uint64(seed & (2 ** 64 - 1)),
+                                                self.ct.c_uint64(off), self.ct.byref(inc), th.cuda.current_device(),
+                                                self.ct.c_void_p(th.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise RuntimeError("ls_randn_torch_compat failed: %s" % self.lib.ls_last_error(None).decode())
+        gen.set_offset(off + inc.value)
+
+    def _matches_torch(self, order):
+        try:
+            state = th.cuda.get_rng_state(self.dev)
+            want = [th.randn_like(t) for t in order]
+            end_torch = th.cuda.get_rng_state(self.dev)
+            th.cuda.set_rng_state(state, self.dev)
+            self._launch()
+            end_ours = th.cuda.get_rng_state(self.dev)
+            same = all(th.equal(a, b) for a, b in zip(order, want)) and th.equal(end_torch, end_ours)
+            th.cuda.set_rng_state(state, self.dev)       # the check consumes no draws
+            return bool(same)
+        except Exception:
+            return False
+
+    def draw(self):
+        self._launch()
+        return self.eps_c, self.eps_u, self.nz
+
+
 def _extract_into_tensor(arr, timesteps, broadcast_shape):
     """fp64 table -> fp32 values gathered at `timesteps`, broadcast to `broadcast_shape`."""
     res = th.from_numpy(arr).to(device=timesteps.device)[timesteps].float()
@@ -435,9 +508,8 @@ class GaussianDiffusion:
                 # full chunks after the first one (whose step-0 noise has x_T's own layout) replay a captured graph
                 if k > 0 and K == chunk and self.graph_draws and type(src) is TorchNoise and not const_noise \
                         and graphed is None:
-                    try:
-                        graphed = eng.graphed_draws(K, B, rag.latent_dim, perm_like, _GraphedDraws)
-                    except RuntimeError:          # capture not possible here (e.g. already capturing): eager draws
+                    graphed = chunk_draws(eng, K, B, rag.latent_dim, perm_like)
+                    if graphed is None:           # neither the fused kernel nor a graph capture is possible: eager draws
                         self.graph_draws = False
                 if graphed is not None and k > 0 and K == chunk:
                     eps_c, eps_u, nzs = graphed.draw()

@@ -55,3 +55,10 @@ for Bs in (256, 512):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     print("SAG decode B=%d: %.2f ms  (%.1f TFLOP/s fp32 algorithmic at 438 MFLOP/clip)" % (Bs, ms, Bs * 438e6 / ms / 1e9))
+
+# which source serves the draws of a full chunk on this box
+from livelyspeaker_b200 import gaussian_diffusion as gd
+perm_like = torch.empty(34, B, 9, 3, device=dev).permute(1, 2, 3, 0)
+srcd = gd.chunk_draws(eng, 16, B, 512, perm_like)
+print("chunk draws served by:", type(srcd).__name__, "(fused kernel verified against torch: %s)"
+      % eng.graphed_draws(16, B, 512, perm_like, gd._FusedDraws).ok)
