@@ -8,7 +8,8 @@ identical numbers.
 Reference:
   scripts/diffusion/gaussian_diffusion.py:240-258    q_sample
   scripts/diffusion/gaussian_diffusion.py:260-282    q_posterior_mean_variance
-  scripts/diffusion/gaussian_diffusion.py:284-399    p_mean_variance (START_X, FIXED_SMALL)
+  scripts/diffusion/gaussian_diffusion.py:284-399    p_mean_variance (START_X, FIXED_SMALL; inpainting blend :314-320)
+  scripts/diffusion/gaussian_diffusion.py:429-481    condition_mean / condition_score (cond_fn hooks)
   scripts/diffusion/gaussian_diffusion.py:507-558    p_sample
   scripts/diffusion/gaussian_diffusion.py:673-743    p_sample_loop_progressive
   scripts/diffusion/gaussian_diffusion.py:745-798    ddim_sample
@@ -68,34 +69,59 @@ def q_sample(tab, x0, i, noise):
     return _pick(tab["sqrt_alphas_cumprod"], i) * x0 + _pick(tab["sqrt_one_minus_alphas_cumprod"], i) * noise
 
 
-def _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised):
+def _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised, hooks=None):
+    """p_mean_variance up to pred_xstart (gaussian_diffusion.py:308-372): model call (two style draws), optional
+    inpainting blend (:314-320; TED re-noises the known motion to level i-1 with a fresh randn_like draw unless
+    i == 0, the BEAT tree blends it as is, scripts_beat/...:319), optional denoised_fn, optional clamp."""
     B = x.shape[0]
     t_orig = torch.full((B,), tmap[i], dtype=torch.long)
     e_c = tape.draw(B, 1, sd["speaker_mu.weight"].shape[0])
     e_u = tape.draw(B, 1, sd["speaker_mu.weight"].shape[0])
     x0 = rag_oracle.cfg_forward(sd, x, t_orig, y, e_c, e_u, nj, nf)
+    hooks = hooks or {}
+    if hooks.get("inpaint") is not None:
+        mask, motion, noised = hooks["inpaint"]
+        if noised and i > 0:
+            motion = q_sample(tab, motion, i - 1, tape.draw_like(motion))
+        x0 = (x0 * ~mask) + (motion * mask)
+    if hooks.get("denoised_fn") is not None:
+        x0 = hooks["denoised_fn"](x0)
     if clip_denoised:
         x0 = x0.clamp(-1, 1)
     return x0
 
 
-def p_sample_step(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised=False, const_noise=False):
+def _cond_grad(hooks, tmap, x, i, y):
+    """cond_fn as SpacedDiffusion calls it: through _WrappedModel, i.e. with the ORIGINAL timestep (respace.py:100-104)."""
+    t_orig = torch.full((x.shape[0],), tmap[i], dtype=torch.long)
+    return hooks["cond_fn"](x, t_orig, y=y)
+
+
+def p_sample_step(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised=False, const_noise=False, hooks=None):
     """One ancestral step.  Returns (sample, pred_xstart)."""
-    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised)
+    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised, hooks)
     mean = _pick(tab["posterior_mean_coef1"], i) * x0 + _pick(tab["posterior_mean_coef2"], i) * x
     log_var = _pick(tab["posterior_log_variance_clipped"], i)
     noise = tape.draw_like(x)      # gaussian_diffusion.py:543 / :787 randn_like(x)
     if const_noise:
         noise = noise[[0]].repeat(x.shape[0], 1, 1, 1)
+    if hooks and hooks.get("cond_fn") is not None:       # condition_mean (:429-442), FIXED_SMALL variance
+        mean = mean.float() + _pick(tab["posterior_variance"], i) * _cond_grad(hooks, tmap, x, i, y).float()
     nz = 0.0 if i == 0 else 1.0
     return mean + nz * torch.exp(0.5 * log_var) * noise, x0
 
 
-def ddim_step(sd, tab, tmap, x, i, y, tape, nj, nf, eta=0.0, clip_denoised=False, const_noise=False):
+def ddim_step(sd, tab, tmap, x, i, y, tape, nj, nf, eta=0.0, clip_denoised=False, const_noise=False, hooks=None):
     """One DDIM step.  Returns (sample, pred_xstart)."""
-    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised)
-    eps = (_pick(tab["sqrt_recip_alphas_cumprod"], i) * x - x0) / _pick(tab["sqrt_recipm1_alphas_cumprod"], i)
+    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised, hooks)
+    x0_ret = x0
+    recip, recipm1 = _pick(tab["sqrt_recip_alphas_cumprod"], i), _pick(tab["sqrt_recipm1_alphas_cumprod"], i)
     ab = _pick(tab["alphas_cumprod"], i)
+    if hooks and hooks.get("cond_fn") is not None:       # condition_score (:456-481)
+        eps = (recip * x - x0) / recipm1
+        eps = eps - (1 - ab).sqrt() * _cond_grad(hooks, tmap, x, i, y)
+        x0 = recip * x - recipm1 * eps
+    eps = (recip * x - x0) / recipm1
     ab_prev = _pick(tab["alphas_cumprod_prev"], i)
     sigma = eta * torch.sqrt((1 - ab_prev) / (1 - ab)) * torch.sqrt(1 - ab / ab_prev)
     noise = tape.draw_like(x)      # gaussian_diffusion.py:543 / :787 randn_like(x)
@@ -103,17 +129,20 @@ def ddim_step(sd, tab, tmap, x, i, y, tape, nj, nf, eta=0.0, clip_denoised=False
         noise = noise[[0]].repeat(x.shape[0], 1, 1, 1)
     mean = x0 * torch.sqrt(ab_prev) + torch.sqrt(1 - ab_prev - sigma ** 2) * eps
     nz = 0.0 if i == 0 else 1.0
-    return mean + nz * sigma * noise, x0
+    return mean + nz * sigma * noise, x0_ret
 
 
 def sample_loop(sd, tab, tmap, shape, y, tape, ddim=False, eta=0.0, clip_denoised=False,
-                skip_timesteps=0, init_image=None, const_noise=False, noise=None, trace=None):
+                skip_timesteps=0, init_image=None, const_noise=False, noise=None, trace=None, hooks=None,
+                const_noise_init=True):
     """p_sample_loop / ddim_sample_loop.  ``trace`` (a list) receives
-    (i, sample, pred_xstart) per step when given."""
+    (i, sample, pred_xstart) per step when given.  ``hooks``: {'inpaint': (mask, motion, noised), 'cond_fn': f,
+    'denoised_fn': g}.  ``const_noise_init`` False = the BEAT tree, whose p_sample_loop_progressive does not repeat
+    the first clip's initial noise (scripts_beat/diffusion/gaussian_diffusion.py:700-704 vs scripts/...:704-708)."""
     B, nj, nf, _ = shape
     n_t = len(tab["betas"])
     img = noise if noise is not None else tape.draw(*shape)
-    if noise is None and const_noise:
+    if noise is None and const_noise and const_noise_init:
         img = img[[0]].repeat(B, 1, 1, 1)
     if skip_timesteps and init_image is None:
         init_image = torch.zeros_like(img)
@@ -124,7 +153,7 @@ def sample_loop(sd, tab, tmap, shape, y, tape, ddim=False, eta=0.0, clip_denoise
     for i in indices:
         kw = {"eta": eta} if ddim else {}
         img, x0 = step(sd, tab, tmap, img, i, y, tape, nj, nf, clip_denoised=clip_denoised,
-                       const_noise=const_noise, **kw)
+                       const_noise=const_noise, hooks=hooks, **kw)
         if trace is not None:
             trace.append((i, img, x0))
     return img
