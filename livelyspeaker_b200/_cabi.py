@@ -200,14 +200,36 @@ class Engine:
         B = audio.shape[0]
         if B > self.max_batch:
             raise LsError("batch %d exceeds the engine's max_batch %d" % (B, self.max_batch))
+        d = self.dims
+        # The kernels stride the audio by cfg.audio_len and origin_x by J*D*34: any other shape would silently read
+        # the wrong rows.  (The reference WavEncoder accepts any length, but RAG.forward's torch.cat only works when
+        # it yields exactly 34 frames - audio_enc.py:22-25, RAG.py:112.)
+        if audio.dim() != 2 or audio.shape[1] != d.audio_len:
+            raise LsError("y['audio_input'] must be [B,%d] for this model (got %s)" % (d.audio_len, tuple(audio.shape)))
         ox_user = y["origin_x"]
+        if tuple(ox_user.shape) != (B, d.njoints, d.nfeats, 34):
+            raise LsError("y['origin_x'] must be [%d,%d,%d,34] (got %s)" % (B, d.njoints, d.nfeats, tuple(ox_user.shape)))
+        if y["vid_indices"].numel() != B:
+            raise LsError("y['vid_indices'] must hold one speaker id per clip (%d), got %d" % (B, y["vid_indices"].numel()))
         inplace = (ox_user.device == self.device and ox_user.dtype == torch.float32 and ox_user.is_contiguous())
         ox = ox_user if inplace else _f32(ox_user, self.device).clone()
-        vid = y["vid_indices"].to(self.device, non_blocking=True).long().contiguous()
+        vid = y["vid_indices"].to(self.device, non_blocking=True).long().reshape(B).contiguous()
         emo, emo_ptr, emo_stride = None, None, 0
         if self.dims.n_pre_emb == 2:
             emo = y["emo"].to(self.device, non_blocking=True).long()
+            if emo.dim() < 1 or emo.shape[0] != B:
+                raise LsError("y['emo'] must be [%d, ...] (got %s)" % (B, tuple(emo.shape)))
             emo_ptr, emo_stride = c_void_p(emo.data_ptr()), emo.stride(0)
+        # nn.Embedding raises IndexError on an out-of-range index (RAG.py:116, scripts_beat/model/RAG.py:125); one
+        # host sync per batch buys the same behaviour instead of a clamped gather
+        lo, hi = int(vid.min()), int(vid.max())
+        if lo < 0 or hi >= self.cfg.n_speakers:
+            raise IndexError("y['vid_indices'] out of range [0,%d): min %d, max %d" % (self.cfg.n_speakers, lo, hi))
+        if emo is not None:
+            e0 = emo.reshape(B, -1)[:, 0]
+            lo, hi = int(e0.min()), int(e0.max())
+            if lo < 0 or hi >= self.cfg.n_emotions:
+                raise IndexError("y['emo'] out of range [0,%d): min %d, max %d" % (self.cfg.n_emotions, lo, hi))
         with torch.cuda.device(self.device):
             self._check(self.lib.ls_precompute_cond(self.h, B, c_void_p(audio.data_ptr()), c_void_p(ox.data_ptr()),
                                                     c_void_p(vid.data_ptr()), emo_ptr, emo_stride, 1, _stream()))
@@ -235,10 +257,21 @@ class Engine:
                                                 c_void_p(out.data_ptr()), _stream()))
         return out
 
+    def _timesteps(self, t, B):
+        """[B] int64 ORIGINAL timesteps on the device, checked against the time-embedding table (the reference indexes
+        pe[timesteps], mlp_module.py:135, and raises on an out-of-range value; the kernels would clamp)."""
+        t = t.to(self.device).long().contiguous()
+        if t.numel() != B:
+            raise LsError("timesteps must be [%d] (got %s)" % (B, tuple(t.shape)))
+        lo, hi = int(t.min()), int(t.max())
+        if lo < 0 or hi >= self.max_timestep:
+            raise IndexError("timestep out of range [0,%d): min %d, max %d" % (self.max_timestep, lo, hi))
+        return t
+
     def model_forward(self, x, t, uncond, style_eps):
         B = x.shape[0]
         x = _f32(x, self.device)
-        t = t.to(self.device).long().contiguous()
+        t = self._timesteps(t, B)
         eps = _f32(style_eps, self.device)
         out = torch.empty(B, self.dims.njoints, self.dims.nfeats, 34, dtype=torch.float32, device=self.device)
         mu = torch.empty(B, 1, self.dims.latent_dim, dtype=torch.float32, device=self.device)
@@ -253,7 +286,7 @@ class Engine:
     def cfg_forward(self, x, t, eps_c, eps_u, scale):
         B = x.shape[0]
         x = _f32(x, self.device)
-        t = t.to(self.device).long().contiguous()
+        t = self._timesteps(t, B)
         eps_c, eps_u, scale = _f32(eps_c, self.device), _f32(eps_u, self.device), _f32(scale, self.device)
         out = torch.empty(B, self.dims.njoints, self.dims.nfeats, 34, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):

@@ -323,6 +323,14 @@ extern "C" int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int
   if (rc) return rc;
   if (!x || !t || !eps_cond || !eps_uncond || !scale || !out) return ls_fail(h, LS_EINVAL, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
+  const int impl = ls_get_impl(h);
+  if (impl == LS_IMPL_TC_BF16X3 || impl == LS_IMPL_TC_BF16) {
+    // the fused tcgen05 kernel in mode 2: both passes + guidance, per-clip timesteps read on the device, no update
+    ls_step_params p{};
+    p.mode = 2;
+    const ls_step_io io{eps_cond, eps_uncond, nullptr, 0, 0, 0, nullptr, out};
+    return lsf_steps(h, B, 1, &p, &io, impl == LS_IMPL_TC_BF16X3, x, scale, s, t);
+  }
   if ((rc = lsk_denoise_simt(h, B, x, t, -1, 3, eps_cond, eps_uncond, h->out_c, h->out_u, s))) return rc;
   return lsk_cfg_combine(h, B, h->out_c, h->out_u, scale, out, s);
 }

@@ -162,11 +162,8 @@ template <int S>
 static int launch_simt(ls_handle* h, int B, const float* x, const int64_t* t, int t_uniform, int pass_mask,
                        const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s) {
   const size_t smem = (size_t)(2 * S * LS_D + S * S + S) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    LS_CUDA(h, cudaFuncSetAttribute(denoise_simt_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  // the attribute is per DEVICE: set on every launch (one process may drive several GPUs)
+  LS_CUDA(h, cudaFuncSetAttribute(denoise_simt_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(B, pass_mask == 3 ? 2 : 1);
   denoise_simt_kernel<S><<<grid, 512, smem, s>>>(h->w, h->JD, h->cfg.n_layers, pass_mask, x, t, t_uniform, h->A, h->P,
                                                  h->z_mu, h->z_lv, h->emo_tok, eps_c, eps_u, out_c, out_u);

@@ -142,6 +142,8 @@ struct FusedParams {
   const float* A; const float* P; const float* z_mu; const float* z_lv; const float* emo_tok;
   const float* x_in; const float* scale;
   int* flags;              // [B] steps completed per clip in this launch (n_steps > 1)
+  const long long* t_dev;  // per-clip ORIGINAL timesteps on the device (ls_cfg_forward, mode 2) or nullptr: sp.t_model
+  int max_t;               // rows of the time-embedding table (t_dev values are clamped into it)
   ls_step_params sp[KMAX];
   StepIO io[KMAX];
   long long* timing;       // debug (LS_FUSED_TIMING=1): clock64 stamps of block 0, threads 0 and 511
@@ -725,6 +727,7 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
       const ls_step_params& sp = p.sp[k];
       const StepIO& io = p.io[k];
       const float* x_t = (k == 0) ? p.x_in : p.io[k - 1].x_prev;
+      const int t_model = p.t_dev ? (int)min(max(p.t_dev[b], 0ll), (long long)(p.max_t - 1)) : sp.t_model;
       if (k > 0) {                  // x of (k-1, b) comes from another CTA
         if (tid == 0)
           while (ld_acquire_gpu(p.flags + b) < k) __nanosleep(64);
@@ -738,7 +741,7 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         float2 ab[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          er[m] = p.w.emb_table[(size_t)sp.t_model * LS_D + c0 + 128 * m];
+          er[m] = p.w.emb_table[(size_t)t_model * LS_D + c0 + 128 * m];
           ab[m] = make_float2(p.w.layer[0].ln1_a[c0 + 128 * m], p.w.layer[0].ln1_b[c0 + 128 * m]);
         }
 #pragma unroll
@@ -1004,6 +1007,8 @@ struct FusedState {
   int KIN = 0, MH = 0, n_stages = 0;
   int sm_count = 0;
   bool attr_done[2][2] = {{false, false}, {false, false}};
+  int max_coresident[2][2] = {{0, 0}, {0, 0}};
+  long long* tbuf = nullptr;   // LS_FUSED_TIMING stamps
 };
 
 template <int S, bool PRECISE>
@@ -1013,13 +1018,33 @@ int launch_fused(ls_handle* h, FusedState* fs, const FusedParams& fp, cudaStream
     LS_CUDA(h, cudaFuncSetAttribute(fused_step_kernel<S, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN));
     done = true;
   }
-  // at most one CTA per SM (all CTAs co-resident: the step counters rely on it); cluster pairs need an even grid
+  // at most one CTA per SM; cluster pairs need an even grid.  max_coresident = occupancy x SMs of THIS context
+  // (MPS / green-context SM limits included): the grid of a multi-step launch never exceeds it.
   const int items = fp.B * fp.n_steps;
+  if (fs->max_coresident[S - 35][PRECISE ? 1 : 0] == 0) {
+    int per_sm = 0;
+    LS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_step_kernel<S, PRECISE>, NT_ALL, SMEM_DYN));
+    if (per_sm < 1) return ls_fail(h, LS_EUNSUPPORTED, "the fused kernel does not fit on an SM of this device");
+    fs->max_coresident[S - 35][PRECISE ? 1 : 0] = per_sm * fs->sm_count;
+  }
 #if LS_MULTICAST
   const int grid = (items + 1 < fs->sm_count ? items + 1 : fs->sm_count) & ~1;
 #else
   const int grid = items < fs->sm_count ? items : fs->sm_count;
 #endif
+  if (fp.n_steps > 1 && grid > fs->max_coresident[S - 35][PRECISE ? 1 : 0])
+    return ls_fail(h, LS_EUNSUPPORTED, "multi-step launch needs %d co-resident CTAs, the device offers %d", grid,
+                   fs->max_coresident[S - 35][PRECISE ? 1 : 0]);
+  if (fp.n_steps > 1) {
+    // CTAs of a multi-step launch wait for each other (per-clip step counters), so the whole grid must be
+    // co-resident: a cooperative launch guarantees it (or fails with cudaErrorCooperativeLaunchTooLarge) even when
+    // other kernels hold SMs - a plain launch could leave producers unscheduled behind spinning consumers.
+    void* args[] = {const_cast<FusedParams*>(&fp)};
+    LS_CUDA(h, cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&fused_step_kernel<S, PRECISE>), dim3(grid),
+                                           dim3(NT_ALL), args, SMEM_DYN, s));
+    h->launches++;
+    return LS_OK;
+  }
   fused_step_kernel<S, PRECISE><<<grid, NT_ALL, SMEM_DYN, s>>>(fp);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
@@ -1036,6 +1061,7 @@ void lsf_destroy(ls_handle* h) {
     if (fs->Sc) cudaFree(fs->Sc);
     if (fs->tc) cudaFree(fs->tc);
     if (fs->flags) cudaFree(fs->flags);
+    if (fs->tbuf) cudaFree(fs->tbuf);
     delete fs;
     h->fused = nullptr;
   }
@@ -1115,7 +1141,7 @@ int lsf_init(ls_handle* h, cudaStream_t s) {
 // n_steps consecutive steps in one launch (n_steps <= LS_MAX_FUSED_STEPS).  Step k reads x from
 // x_in (k = 0) or io[k-1].x_prev, so with n_steps > 1 every step needs its own x_prev buffer.
 int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const ls_step_io* io, int precise,
-              const float* x_in, const float* scale, cudaStream_t s) {
+              const float* x_in, const float* scale, cudaStream_t s, const int64_t* t_dev) {
   FusedState* fs = static_cast<FusedState*>(h->fused);
   if (!fs) return ls_fail(h, LS_EUNSUPPORTED, "tcgen05 path not available");
   if (n_steps < 1 || n_steps > KMAX) return ls_fail(h, LS_EINVAL, "n_steps %d outside [1,%d]", n_steps, KMAX);
@@ -1123,7 +1149,7 @@ int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const l
     // With one clip the two CTAs of a cluster would hold consecutive steps of the SAME clip: the second waits
     // for the first, which in turn needs its peer to drain the shared weight ring.  Run step by step.
     for (int k = 0; k < n_steps; ++k) {
-      const int rc = lsf_steps(h, B, 1, p + k, io + k, precise, k == 0 ? x_in : io[k - 1].x_prev, scale, s);
+      const int rc = lsf_steps(h, B, 1, p + k, io + k, precise, k == 0 ? x_in : io[k - 1].x_prev, scale, s, t_dev);
       if (rc != LS_OK) return rc;
     }
     return LS_OK;
@@ -1141,6 +1167,8 @@ int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const l
   fp.A = h->A; fp.P = h->P; fp.z_mu = h->z_mu; fp.z_lv = h->z_lv; fp.emo_tok = h->emo_tok;
   fp.x_in = x_in; fp.scale = scale;
   fp.flags = fs->flags;
+  fp.t_dev = reinterpret_cast<const long long*>(t_dev);
+  fp.max_t = h->cfg.max_timestep;
   for (int k = 0; k < n_steps; ++k) {
     fp.sp[k] = p[k];
     fp.io[k].eps_c = io[k].eps_cond; fp.io[k].eps_u = io[k].eps_uncond; fp.io[k].noise = io[k].noise;
@@ -1149,7 +1177,7 @@ int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const l
   }
   if (n_steps > 1) LS_CUDA(h, cudaMemsetAsync(fs->flags, 0, (size_t)B * sizeof(int), s));
   fp.timing = nullptr;
-  static long long* tbuf = nullptr;
+  long long*& tbuf = fs->tbuf;        // per handle (= per device)
   const bool timing = getenv("LS_FUSED_TIMING") != nullptr;
   if (timing) {
     if (!tbuf) cudaMalloc(&tbuf, 512 * sizeof(long long));

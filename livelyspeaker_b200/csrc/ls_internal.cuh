@@ -127,5 +127,6 @@ int lsw_conv(ls_handle* h, int layer, const float* in, const float* bias, float*
 int lsf_init(ls_handle* h, cudaStream_t s);            // build bf16 weight tapes; 0 if available
 void lsf_destroy(ls_handle* h);
 int lsf_available(const ls_handle* h);
+// t_dev: per-clip ORIGINAL timesteps on the device (then p->t_model is ignored; mode 2 callers) or nullptr
 int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const ls_step_io* io, int precise,
-              const float* x_in, const float* scale, cudaStream_t s);
+              const float* x_in, const float* scale, cudaStream_t s, const int64_t* t_dev = nullptr);

@@ -254,11 +254,8 @@ __global__ void __launch_bounds__(512) cond_proj_kernel(LsWeights w, int JD, int
 int lsk_cond_proj(ls_handle* h, int B, int b0, const float* af_cm, float* origin_x, const int64_t* vid,
                   const int64_t* emo, int64_t emo_stride, int mutate_origin, cudaStream_t s) {
   const size_t smem = (size_t)(LS_AF * LS_F + h->JD * LS_NPRE + LS_SPK) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    LS_CUDA(h, cudaFuncSetAttribute(cond_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
-  }
+  // the attribute is per DEVICE: set on every launch (one process may drive several GPUs)
+  LS_CUDA(h, cudaFuncSetAttribute(cond_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   cond_proj_kernel<<<B, 512, smem, s>>>(h->w, h->JD, h->cfg.n_speakers, h->cfg.n_emotions, af_cm, origin_x, vid, emo,
                                         emo_stride, mutate_origin, b0, h->A, h->P, h->z_mu, h->z_lv, h->emo_tok);
   LS_LAUNCH_CHECK(h);

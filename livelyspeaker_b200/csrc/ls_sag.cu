@@ -240,13 +240,10 @@ extern "C" int ls_sag_decode(const ls_sag_weights* w, int32_t B, const float* x,
       w->n_layers > LS_SAG_MAX_LAYERS || w->n_pre_poses < 0 || w->n_pre_poses > T)
     return ls_fail(nullptr, LS_EUNSUPPORTED, "ls_sag_decode: built for 34 frames, d=512, ff=1024, 4 heads, <= %d layers",
                    LS_SAG_MAX_LAYERS);
-  static bool attr_done = false;
   const int smem = SMEM_FLOATS * (int)sizeof(float);
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(sag_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
-      return ls_fail(nullptr, LS_ECUDA, "ls_sag_decode: cannot reserve %d bytes of shared memory", smem);
-    attr_done = true;
-  }
+  // the attribute is per DEVICE: set on every launch (one process may drive several GPUs)
+  if (cudaFuncSetAttribute(sag_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return ls_fail(nullptr, LS_ECUDA, "ls_sag_decode: cannot reserve %d bytes of shared memory", smem);
   sag_decode_kernel<<<B, 512, smem, (cudaStream_t)stream>>>(*w, x, z, mask, out);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_sag_decode: %s", cudaGetErrorString(e));

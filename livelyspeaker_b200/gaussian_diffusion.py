@@ -5,17 +5,20 @@ attribute tables) for the SAMPLING path: schedules (:26-70), derived fp64 tables
 (:167-204), q_sample (:240-258), q_posterior_mean_variance (:260-282),
 p_mean_variance (:284-399), p_sample (:507-558), p_sample_loop[_progressive]
 (:608-743), ddim_sample (:745-798), ddim_sample_loop[_progressive] (:895-1014),
-condition_mean / condition_score (:429-481), _extract_into_tensor (:1651-1664).
-Training losses, VLB terms, PLMS and the *_with_grad samplers are outside the
-hot path and raise NotImplementedError.
+condition_mean / condition_score (:429-481), plms_sample[_loop] (:1016-1211),
+_extract_into_tensor (:1651-1664).  Training losses, VLB terms and the *_with_grad
+samplers (they need autograd through the denoiser) are outside the hot path
+ and raise NotImplementedError.
 
 Two execution routes:
   * fused  - the model is this package's ClassifierFreeSampleModel(RAG) and no Python
     hook (cond_fn / denoised_fn / inpainting) is active: each step is ONE C-ABI call
     (`ls_step`: both denoiser passes + guidance + sampler update).  This is what the
     shipped eval scripts exercise.
-  * generic - anything else: the model is called like in the reference and the
-    sampler arithmetic uses torch elementwise ops on the device.
+  * generic - anything else (cond_fn, denoised_fn, inpainting, PLMS, foreign models): the
+    model is called like in the reference - for this package's CFG wrapper that is ONE
+    launch of the same fused tcgen05 kernel in mode 2 (x0 only, per-clip timesteps read on
+    the device) - and the sampler arithmetic uses torch elementwise ops on the device.
 
 Random draws are made with torch in exactly the reference's order AND memory layout
 (see `_LikeLayouts`), so the same seed on the same device yields the same numbers.
@@ -203,6 +206,22 @@ class _FusedDraws:
     def draw(self):
         self._launch()
         return self.eps_c, self.eps_u, self.nz
+
+
+class _exact_denoiser:
+    """Context: this package's CFG-wrapped RAG in implementation 'auto' runs its fp32 SIMT denoiser inside the block."""
+
+    def __init__(self, model, on):
+        inner = getattr(model, "model", None)
+        self.rag = inner if (on and hasattr(inner, "set_impl") and getattr(inner, "impl", None) == "auto") else None
+
+    def __enter__(self):
+        if self.rag is not None:
+            self.rag.set_impl("simt")
+
+    def __exit__(self, *exc):
+        if self.rag is not None:
+            self.rag.set_impl("auto")
 
 
 def _extract_into_tensor(arr, timesteps, broadcast_shape):
@@ -439,7 +458,7 @@ class GaussianDiffusion:
             img = noise
         else:
             img = src.randn(tuple(shape), device)
-            if const_noise:
+            if const_noise and getattr(self, "const_noise_init", True):
                 img = img[[0]].repeat(img.shape[0], 1, 1, 1)
         if skip_timesteps and init_image is None:
             init_image = th.zeros_like(img)
@@ -611,11 +630,18 @@ class GaussianDiffusion:
             return self._predict_eps_from_xstart(x_, t_, out_["pred_xstart"]), out_, orig
 
         ab_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, x.shape)
-        eps, out, out_orig = model_eps(x, t)
+        # The order-4 Adams-Bashforth extrapolation multiplies the denoiser's error by (55+59+37+9)/24 = 6.7 on top of
+        # the 1/sqrt(1/abar - 1) of the eps re-derivation: the ~1e-5 relative error of the bf16x3 tensor-core denoiser
+        # then brushes the parity bar (measured 1.2e-4 on 1 of 1836 elements), so order 4 calls the fp32 SIMT denoiser.
+        # Orders <= 3 (factors 2 / 3.7) run the fused tcgen05 kernel like every other generic-route call.
+        with _exact_denoiser(model, order >= 4):
+            eps, out, out_orig = model_eps(x, t)
+            eps_2 = None
+            if order > 1 and old_out is None:
+                mean_pred = out["pred_xstart"] * th.sqrt(ab_prev) + th.sqrt(1 - ab_prev) * eps
+                eps_2, _, _ = model_eps(mean_pred, t - 1)
         if order > 1 and old_out is None:        # first step: pseudo improved Euler (second model call at t - 1)
             old_eps = [eps]
-            mean_pred = out["pred_xstart"] * th.sqrt(ab_prev) + th.sqrt(1 - ab_prev) * eps
-            eps_2, _, _ = model_eps(mean_pred, t - 1)
             eps_prime = (eps + eps_2) / 2
         else:                                    # Adams-Bashforth; order 1 on the first step fails like the reference
             old_eps = old_out["old_eps"]

@@ -48,9 +48,10 @@ def create_gaussian_diffusion(args, timestep_respacing='', variant='ted'):
         rescale_timesteps=False,
         lambda_vel=args.lambda_vel, lambda_rcxyz=args.lambda_rcxyz, lambda_fc=args.lambda_fc)
     if variant == 'beat':
-        # the BEAT tree's sampler differs in three observable ways
-        # (scripts_beat/diffusion/gaussian_diffusion.py:319, 665, 913-914)
+        # the BEAT tree's sampler differs in four observable ways
+        # (scripts_beat/diffusion/gaussian_diffusion.py:319, 665, 700-704, 913-914)
         diffusion.dump_key = "sample"
         diffusion.allow_ddim_const_noise = False
         diffusion.inpaint_noised = False
+        diffusion.const_noise_init = False   # scripts_beat/...:700-704: x_T is NOT repeated under const_noise
     return diffusion

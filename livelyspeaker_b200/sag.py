@@ -132,7 +132,9 @@ class Decoder_TRANSFORMER(nn.Module):
                                    c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc != 0:
             raise _cabi.LsError("libls_b200 error %d: %s" % (rc, lib.ls_last_error(None).decode()))
-        batch["txt_output" if use_text_emb else "output"] = out
+        # the reference returns output.permute(1, 2, 3, 0) of a [F,B,J,D] tensor (motionclip_module.py:181): same
+        # values, memory order [F,B,J,D] - it decides the element order of a later randn_like(init_image)
+        batch["txt_output" if use_text_emb else "output"] = _cabi._ref_layout(out)
         return batch
 
 

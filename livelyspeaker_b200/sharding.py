@@ -8,7 +8,9 @@ the batch, run the loop with NO per-step communication, and one all_gather of th
 
 RNG: `SlicedNoise` makes rank r reproduce rows [lo, hi) of the draws a single-process
 run at the global batch would make with the same seed, so a sharded run equals the
-1-GPU run bit for bit; the cheaper default is an independent stream per rank.
+1-GPU run bit for bit; the cheaper default (rng='per_rank') is an independent stream per
+rank: rank r > 0 re-seeds its generator with seed + r before sampling (fork_seed=False
+keeps the caller's own seeding).
 """
 import torch
 import torch.distributed as dist
@@ -65,11 +67,11 @@ def all_gather_samples(local, batch, group=None):
     world = dist.get_world_size(group)
     sizes = [shard_bounds(batch, world, r) for r in range(world)]
     biggest = max(hi - lo for lo, hi in sizes)
-    pad = local
+    pad = local.contiguous()      # generic-route results carry the permuted [F,B,J,D] layout: NCCL wants dense tensors
     if local.shape[0] < biggest:
-        pad = torch.cat([local, local.new_zeros((biggest - local.shape[0],) + tuple(local.shape[1:]))], 0)
-    bucket = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(bucket, pad.contiguous(), group=group)
+        pad = torch.cat([pad, pad.new_zeros((biggest - pad.shape[0],) + tuple(pad.shape[1:]))], 0)
+    bucket = [torch.empty(pad.shape, dtype=pad.dtype, device=pad.device) for _ in range(world)]
+    dist.all_gather(bucket, pad, group=group)
     return torch.cat([b[:hi - lo] for b, (lo, hi) in zip(bucket, sizes)], 0)
 
 
@@ -86,17 +88,33 @@ def sample_sharded(sample_fn, model, shape, model_kwargs, diffusion=None, rng="p
     for k in ("noise", "init_image"):
         if kwargs.get(k) is not None:
             kwargs[k] = kwargs[k][lo:hi]
-    saved = None
+    saved = saved_model = None
+    if rng == "per_rank" and kwargs.pop("fork_seed", True) and rank > 0:
+        # The reference seeds every process alike (fixseed, scripts/test_RAG_ted.py:146): identical streams would give
+        # every shard the same x_T and noise.  Ranks > 0 therefore advance to their own stream (seed + rank).
+        dev = next(model.parameters()).device
+        if dev.type == "cuda":
+            torch.cuda.manual_seed((torch.cuda.initial_seed() + rank) % (2 ** 63))
+        else:
+            torch.manual_seed((torch.initial_seed() + rank) % (2 ** 63))
+    else:
+        kwargs.pop("fork_seed", None)
     if rng == "global_slice":
         if diffusion is None:
             raise ValueError("rng='global_slice' needs the diffusion object")
         saved = diffusion.noise_source
         diffusion.noise_source = SlicedNoise(saved, B, lo, hi)
+        # on the generic route the CFG wrapper draws its two style tensors itself (cfg_sampler.py): slice those too
+        if hasattr(model, "noise_source"):
+            saved_model = (model.noise_source,)
+            model.noise_source = SlicedNoise(model.noise_source if model.noise_source is not None else saved, B, lo, hi)
     try:
         local = sample_fn(model, (hi - lo,) + tuple(shape[1:]), model_kwargs=local_kwargs, **kwargs)
     finally:
         if saved is not None:
             diffusion.noise_source = saved
+        if saved_model is not None:
+            model.noise_source = saved_model[0]
     if not gather:
         return local
     return all_gather_samples(local, B, group)

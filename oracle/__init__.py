@@ -5,7 +5,7 @@ path, torch-CPU fp32 for the denoiser and the sampler update) of the reference
 algorithm.  It exists so that the CUDA product path in ``livelyspeaker_b200``
 can be checked against something that was itself pinned to the reference.
 
-Rules (enforced by tests/test_layout_rules.py):
+Rules (enforced by tests/test_host_logic.py::test_product_never_imports_oracle_or_reference):
   * only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
     ``--impl reference`` legs of ``bench.py`` may import anything from here;
   * nothing under ``livelyspeaker_b200/`` imports it - the product path fails

@@ -50,3 +50,9 @@ def golden_sag():
 @pytest.fixture(scope="session")
 def golden_schedule():
     return dict(np.load(os.path.join(GOLDEN, "schedule.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_hooks():
+    return {"ted": dict(np.load(os.path.join(GOLDEN, "hooks_ted.npz"))),
+            "beat": dict(np.load(os.path.join(GOLDEN, "hooks_beat.npz")))}

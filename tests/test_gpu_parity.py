@@ -469,3 +469,228 @@ def test_error_paths():
         n = ls.MAX_FUSED_STEPS + 1
         buf = torch.empty(n, 2, 9, 3, 34, device=DEV)
         eng.step_multi([ok] * n, xg, [z] * n, [z] * n, [xg] * n, y["scale"], buf, None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Round 2: the branches the round-1 suite left uncovered: hooked samplers, BEAT ancestral loops,
+# full-size multi-step chunks against the oracle, config 3 end to end, concurrency of the multi-step launch.
+# ---------------------------------------------------------------------------------------------------------------
+from test_oracle_golden import HOOK_TAGS, _hook_cases, few_threads, run_oracle_hooks
+
+
+def _maxerr(got, want):
+    return float((got.detach().cpu().double() - torch.as_tensor(np.asarray(want)).double()).abs().max())
+
+
+@pytest.mark.parametrize("name,tag", HOOK_TAGS)
+def test_hooked_and_beat_loops_vs_reference_fixtures(name, tag, golden_hooks):
+    """Inpainting blend, cond_fn (condition_mean / condition_score), denoised_fn - the generic route, whose model call
+    is the fused kernel in mode 2 - and the BEAT tree's ancestral loops (fused route), against the reference's own
+    outputs (tests/golden/make_golden_hooks.py) and the oracle on the recorded draws."""
+    mod, cases = _hook_cases(name)
+    spec, ddim, seed, kw = cases[tag]
+    dims, sd, cfg, diffusion = build(name, spec)
+    want, tape = run_oracle_hooks(name, tag, dims, sd)
+    y_extra, cond_fn, denoised_fn, _ = mod.hook_objects(kw.get("hooks", ()), dims, 2, noised=(name == "ted"))
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    y.update({k: v.to(DEV) for k, v in y_extra.items()})
+    diffusion.noise_source = cfg.noise_source = ls.ReplayNoise(tape.record)
+    fn = diffusion.ddim_sample_loop if ddim else diffusion.p_sample_loop
+    extra = {"eta": kw["eta"]} if "eta" in kw else {}
+    got = fn(cfg, (2, dims.njoints, dims.nfeats, 34), clip_denoised=kw.get("clip_denoised", False),
+             model_kwargs={"y": y}, skip_timesteps=kw.get("skip_timesteps", 0), cond_fn=cond_fn,
+             denoised_fn=denoised_fn, const_noise=kw.get("const_noise", False), **extra)
+    assert diffusion.noise_source.pos == len(tape.record)
+    _close(got, golden_hooks[name]["loop_" + tag])
+    _close(got, want)
+
+
+def _chunk_draws(shape, n_steps, seed, first_like=None):
+    """The draws of an n-step loop in the reference's order: x_T, then per step (cond style, uncond style, step noise;
+    the step noise in [F,B,J,D] memory order from the second step on)."""
+    B, J, D, F = shape
+    tape = sampler_oracle.NoiseTape(seed=seed)
+    tape.draw(*shape)
+    perm = torch.empty(F, B, J, D).permute(1, 2, 3, 0)
+    for k in range(n_steps):
+        tape.draw(B, 1, 512)
+        tape.draw(B, 1, 512)
+        tape.draw_like((first_like if first_like is not None else torch.empty(*shape)) if k == 0 else perm)
+    return tape.record
+
+
+@pytest.mark.parametrize("name,B", [("ted", 512), ("beat", 256)])
+def test_full_size_16_step_chunk_vs_oracle(name, B):
+    """BASELINE configs 2 / 4 at full batch: the last 16 iterations of the T=1000 ancestral loop as ONE ls_step_multi
+    launch (items of several rounds, clips hopping between SMs) against the oracle on 8 scattered clips."""
+    dims, sd, cfg, diffusion = build(name, "")
+    shape = (B, dims.njoints, dims.nfeats, 34)
+    K = 16
+    rec = _chunk_draws(shape, K, seed=500 + B)
+    diffusion.noise_source = ls.ReplayNoise(rec)
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    launches0 = cfg.model.engine(B).launch_count()
+    got = diffusion.p_sample_loop(cfg, shape, clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=1000 - K)
+    idx = torch.tensor([0, 1, B // 3, B // 2 - 1, B // 2, B - 150, B - 2, B - 1])
+    yc = {k: (v[idx].clone() if torch.is_tensor(v) else v) for k, v in synthetic.synth_cond(dims, B).items()}
+    tab, tmap = schedule_oracle.build("cosine", 1000, "")
+    tape = sampler_oracle.NoiseTape(replay=[t[idx] for t in rec])
+    with torch.no_grad():
+        want = sampler_oracle.sample_loop(sd, tab, tmap, (len(idx),) + shape[1:], yc, tape, skip_timesteps=1000 - K)
+    print("max |gpu - oracle| over 8 clips x 16 steps (%s, B=%d): %.3g" % (name, B, _maxerr(got[idx.to(DEV)], want)))
+    _close(got[idx.to(DEV)], want)
+    assert torch.isfinite(got).all()
+
+
+def test_config3_sag_init_image_b256_vs_oracle_and_same_seed(golden_sag):
+    """BASELINE config 3 (scripts/test_LivelySpeaker_ted.py:85-113, 212): SAG decoder -> init_image -> ddim100 loop with
+    skip_timesteps=80 at B=256, against the oracle (SAG oracle + sampler oracle) on 6 scattered clips; then the same-seed
+    property with the decoder's output as init_image (its [F,B,J,D] memory order decides the first randn_like)."""
+    from oracle import sag_oracle
+    sd_sag = synthetic.synth_sag_state_dict(seed=3)
+    dec = ls.Decoder_TRANSFORMER(latent_dim=512, n_pre_poses=4, use_style=False)
+    dec.load_state_dict(sd_sag, strict=True)
+    dec = dec.to(DEV).eval()
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    B = 256
+    g = torch.Generator().manual_seed(31)
+    xb, zb = 0.3 * torch.randn(B, 9, 3, 34, generator=g), torch.randn(B, 512, generator=g)
+    mb = torch.ones(B, 34, dtype=torch.bool)
+    init = dec({"x": xb.to(DEV), "z": zb.to(DEV), "mask": mb.to(DEV)})["output"]
+    assert init.stride() == torch.empty(34, B, 9, 3).permute(1, 2, 3, 0).stride()     # motionclip_module.py:181
+    shape = (B, 9, 3, 34)
+    rec = _chunk_draws(shape, 20, seed=77, first_like=torch.empty(34, B, 9, 3).permute(1, 2, 3, 0))
+    diffusion.noise_source = ls.ReplayNoise(rec)
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    got = diffusion.ddim_sample_loop(cfg, shape, clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=80,
+                                     init_image=init)
+    idx = torch.tensor([0, 63, 64, 128, 200, 255])
+    yc = {k: (v[idx].clone() if torch.is_tensor(v) else v) for k, v in synthetic.synth_cond(dims, B).items()}
+    tab, tmap = schedule_oracle.build("cosine", 1000, "ddim100")
+    with torch.no_grad():
+        init_o = sag_oracle.decode(sd_sag, xb[idx], zb[idx], mb[idx])
+        tape = sampler_oracle.NoiseTape(replay=[t[idx] for t in rec])
+        want = sampler_oracle.sample_loop(sd, tab, tmap, (len(idx), 9, 3, 34), yc, tape, ddim=True, skip_timesteps=80,
+                                          init_image=init_o)
+    print("config 3, B=256: max |gpu - oracle| = %.3g" % _maxerr(got[idx.to(DEV)], want))
+    _close(got[idx.to(DEV)], want)
+    # same seed, torch's own generator: product vs the oracle run on the GPU's generator, decoder output as init_image
+    init3 = dec({"x": xb[:3].to(DEV), "z": zb[:3].to(DEV), "mask": mb[:3].to(DEV)})["output"]
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+
+    class CudaTape(sampler_oracle.NoiseTape):
+        def __init__(self):
+            self.replay, self.record, self.gen, self.device = None, [], None, DEV
+
+        def draw(self, *s):
+            self.record.append(torch.randn(*s, device=DEV))
+            return self.record[-1]
+
+        def draw_like(self, x):
+            self.record.append(torch.randn_like(x))
+            return self.record[-1]
+
+    orig_pick = sampler_oracle._pick
+    sampler_oracle._pick = lambda table, i: orig_pick(table, i).to(DEV)
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.manual_seed(78)
+        with torch.no_grad():
+            want3 = sampler_oracle.sample_loop(sd_dev, tab, tmap, (3, 9, 3, 34), synthetic.synth_cond(dims, 3, device=DEV),
+                                               CudaTape(), ddim=True, skip_timesteps=94, init_image=init3.clone())
+    finally:
+        sampler_oracle._pick = orig_pick
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    diffusion.noise_source = ls.TorchNoise()
+    torch.manual_seed(78)
+    got3 = diffusion.ddim_sample_loop(cfg, (3, 9, 3, 34), clip_denoised=False,
+                                      model_kwargs={"y": synthetic.synth_cond(dims, 3, device=DEV)}, skip_timesteps=94,
+                                      init_image=init3)
+    _close(got3, want3)
+
+
+@pytest.mark.timeout(300)
+def test_multi_step_launch_next_to_a_busy_stream():
+    """The multi-step launch is cooperative (all CTAs co-resident or not started): kernels running on another stream
+    must not be able to starve a producer CTA behind spinning consumers.  Same results as the launch on an idle GPU."""
+    dims, sd, cfg, diffusion = build("ted", "")
+    B, K = 300, 16
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    eng = cfg.model.engine(B)
+    eng.set_cond(y, force=True)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, 9, 3, 34, generator=g).to(DEV)
+    e_c = [torch.randn(B, 1, 512, generator=g).to(DEV) for _ in range(K)]
+    e_u = [torch.randn(B, 1, 512, generator=g).to(DEV) for _ in range(K)]
+    nz = [torch.randn(B, 9, 3, 34, generator=g).to(DEV) for _ in range(K)]
+    params = [diffusion.step_params(i, ddim=False, clip_denoised=False) for i in range(K - 1, -1, -1)]
+    ref = torch.empty(K, B, 9, 3, 34, device=DEV)
+    eng.step_multi(params, x, e_c, e_u, nz, y["scale"], ref, None)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    a = torch.randn(4096, 4096, device=DEV)
+    small = torch.zeros(1 << 20, device=DEV)
+    outs = [torch.empty_like(ref) for _ in range(6)]
+    with torch.cuda.stream(side):
+        for _ in range(150):                # ~tens of ms of matmuls and many small kernels racing for SMs
+            a = torch.tanh(a @ a * 1e-3)
+            small.add_(1.0)
+    for o in outs:
+        eng.step_multi(params, x, e_c, e_u, nz, y["scale"], o, None)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o, ref)
+
+
+def test_cfg_forward_runs_the_fused_kernel_and_matches_simt():
+    """ls_cfg_forward (ClassifierFreeSampleModel.forward) with per-clip timesteps: the tcgen05 kernel in mode 2 against
+    the fp32 SIMT denoiser, batch-mixed timesteps."""
+    dims, sd, cfg, _ = build("ted", "")
+    B = 37
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 9, 3, 34, generator=g).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=g).to(DEV)
+    e_c, e_u = torch.randn(B, 1, 512, generator=g).to(DEV), torch.randn(B, 1, 512, generator=g).to(DEV)
+    outs = {}
+    for impl in ("simt", "auto"):
+        cfg.model.set_impl(impl)
+        eng = cfg.model.engine(B)
+        eng.set_cond(y, force=True)
+        n0 = eng.launch_count()
+        outs[impl] = eng.cfg_forward(x, t, e_c, e_u, y["scale"])
+        outs[impl + "_launches"] = eng.launch_count() - n0
+    assert outs["auto_launches"] == 1            # both passes + guidance in one launch
+    _close(outs["auto"], outs["simt"])
+    yc = synthetic.synth_cond(dims, B)
+    with torch.no_grad():
+        want = rag_oracle.cfg_forward(sd, x.cpu(), t.cpu(), yc, e_c.cpu(), e_u.cpu(), 9, 3)
+    _close(outs["auto"], want)
+
+
+def test_input_validation():
+    """Shapes and index ranges the kernels rely on are checked at the boundary."""
+    from livelyspeaker_b200._cabi import LsError
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    eng = cfg.model.engine(2)
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    bad = dict(y)
+    bad["audio_input"] = y["audio_input"][:, :-5]
+    with pytest.raises(LsError):
+        eng.set_cond(bad, force=True)
+    bad = dict(y)
+    bad["origin_x"] = y["origin_x"][:, :, :, :30]
+    with pytest.raises(LsError):
+        eng.set_cond(bad, force=True)
+    bad = dict(y)
+    bad["vid_indices"] = torch.tensor([3, 1400], device=DEV)
+    with pytest.raises(IndexError):
+        eng.set_cond(bad, force=True)
+    eng.set_cond(y, force=True)
+    x = torch.zeros(2, 9, 3, 34, device=DEV)
+    z = torch.zeros(2, 1, 512, device=DEV)
+    with pytest.raises(IndexError):
+        eng.cfg_forward(x, torch.tensor([5, 1000], device=DEV), z, z, y["scale"])
+    with pytest.raises(IndexError):
+        eng.model_forward(x, torch.tensor([-1, 3], device=DEV), False, z)

@@ -1,5 +1,7 @@
 """The oracle against the fixtures the REFERENCE produced (tests/golden/make_golden.py).
 This is what licenses using oracle/ as the checker in the GPU parity tests."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -9,6 +11,21 @@ from livelyspeaker_b200 import synthetic
 from oracle import rag_oracle, sampler_oracle, schedule_oracle
 
 TIGHT = dict(rtol=1e-5, atol=2e-5)     # oracle vs reference: same fp32 ops, same order
+
+
+class few_threads:
+    """Small-batch oracle loops are thousands of tiny ops: with all cores torch spends its time in thread hand-offs
+    (B=1, T=1000: 164 s on 8 threads, 25 s on 2).  Results do not depend on the thread count."""
+
+    def __init__(self, n=2):
+        self.n = n
+
+    def __enter__(self):
+        self.saved = torch.get_num_threads()
+        torch.set_num_threads(self.n)
+
+    def __exit__(self, *exc):
+        torch.set_num_threads(self.saved)
 
 
 def _close(a, b, **kw):
@@ -97,6 +114,7 @@ LOOPS = {   # tag: (respacing, steps, ddim, seed, batch, kwargs)
     "anc100_constnoise": ("100", 1000, False, 237, 2, {"const_noise": True}),
     "anc100_skip60": ("100", 1000, False, 238, 2, {"skip_timesteps": 60}),
     "t100_b1": ("", 100, False, 239, 1, {}),
+    "anc1000_b1": ("", 1000, False, 240, 1, {}),      # the headline configuration's loop: T=1000 ancestral
 }
 
 
@@ -106,14 +124,14 @@ def run_oracle_loop(tag, g, dims, sd):
     tab, tmap = schedule_oracle.build("cosine", steps, spec)
     init = torch.from_numpy(g["init_image"]) if kw.pop("init", False) else None
     tape = sampler_oracle.NoiseTape(seed=seed)
-    with torch.no_grad():
+    with torch.no_grad(), few_threads():
         out = sampler_oracle.sample_loop(sd, tab, tmap, (B, dims.njoints, dims.nfeats, 34),
                                          synthetic.synth_cond(dims, B), tape, ddim=ddim, init_image=init, **kw)
     return out, tape
 
 
 @pytest.mark.parametrize("tag", ["ddim100", "anc100", "ddim100_sdedit", "ddim100_eta05_clip", "anc100_constnoise",
-                                 "anc100_skip60", "t100_b1"])
+                                 "anc100_skip60", "t100_b1", "anc1000_b1"])
 def test_whole_loops_ted(tag, golden_ted, ted):
     dims, sd = ted
     out, tape = run_oracle_loop(tag, golden_ted, dims, sd)
@@ -136,7 +154,7 @@ def run_oracle_plms(tag, g, dims, sd):
     tab, tmap = schedule_oracle.build("cosine", 1000, spec)
     init = torch.from_numpy(g["init_image"]) if kw.pop("init", False) else None
     tape = sampler_oracle.NoiseTape(seed=seed)
-    with torch.no_grad():
+    with torch.no_grad(), few_threads():
         out = sampler_oracle.plms_loop(sd, tab, tmap, (2, dims.njoints, dims.nfeats, 34), synthetic.synth_cond(dims, 2),
                                        tape, order=order, init_image=init, **kw)
     return out, tape
@@ -179,3 +197,45 @@ def test_noise_tape_layout_rule():
     torch.manual_seed(3)
     b = torch.randn_like(x)
     assert torch.equal(a, b) and a.stride() == x.stride()
+
+
+# ---- hooked branches: inpainting, cond_fn, denoised_fn, BEAT ancestral (tests/golden/make_golden_hooks.py) ----------
+sys_path_golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _hook_cases(name):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_hooks_cases", os.path.join(sys_path_golden, "hook_cases.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, (mod.CASES_TED if name == "ted" else mod.CASES_BEAT)
+
+
+def run_oracle_hooks(name, tag, dims, sd, B=2):
+    mod, cases = _hook_cases(name)
+    spec, ddim, seed, kw = cases[tag]
+    tab, tmap = schedule_oracle.build("cosine", 1000, spec)
+    _, _, _, hooks = mod.hook_objects(kw.get("hooks", ()), dims, B, noised=(name == "ted"))
+    tape = sampler_oracle.NoiseTape(seed=seed)
+    with torch.no_grad(), few_threads():
+        out = sampler_oracle.sample_loop(sd, tab, tmap, (B, dims.njoints, dims.nfeats, 34), synthetic.synth_cond(dims, B),
+                                         tape, ddim=ddim, eta=kw.get("eta", 0.0),
+                                         clip_denoised=kw.get("clip_denoised", False),
+                                         skip_timesteps=kw.get("skip_timesteps", 0),
+                                         const_noise=kw.get("const_noise", False), hooks=hooks,
+                                         const_noise_init=(name == "ted"))
+    return out, tape
+
+
+HOOK_TAGS = [("ted", t) for t in ("inp_anc", "inp_ddim", "cond_anc", "cond_ddim", "dfn_anc_clip", "all_anc")] + \
+            [("beat", t) for t in ("anc100", "anc100_constnoise", "inp_anc", "anc1000_tail")]
+
+
+@pytest.mark.parametrize("name,tag", [("ted", "inp_ddim"), ("ted", "cond_ddim"), ("ted", "all_anc"),
+                                      ("beat", "anc100_constnoise"), ("beat", "inp_anc")])
+def test_hooked_loops(name, tag, golden_hooks):
+    """Oracle vs the reference's own outputs on the hooked branches (gaussian_diffusion.py:314-320, 429-481)."""
+    dims = synthetic.dims_for(name)
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    out, _ = run_oracle_hooks(name, tag, dims, sd)
+    _close(out, golden_hooks[name]["loop_" + tag])

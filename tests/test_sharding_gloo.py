@@ -65,9 +65,18 @@ def _worker(rank, world, port, B, ret):
         torch.manual_seed(100 + rank)
         out2 = sharding.sample_sharded(d.ddim_sample_loop, toy, shape, {"y": y}, rng="per_rank",
                                        clip_denoised=False, skip_timesteps=97, eta=0.0)
+        # per_rank: every rank seeded alike (the reference's fixseed) and identical conditioning in every clip - only the
+        # rank-dependent re-seed of sample_sharded can make the shards differ; fork_seed=False keeps them identical
+        y_same = {"scale": torch.ones(B), "audio_input": torch.zeros(B, 4)}
+        outs3 = []
+        for fork in (True, False):
+            torch.manual_seed(55)
+            outs3.append(sharding.sample_sharded(d.p_sample_loop, toy, shape, {"y": y_same}, rng="per_rank",
+                                                 fork_seed=fork, clip_denoised=False, skip_timesteps=97))
         if rank == 0:
             ret["sharded"] = out.clone()
             ret["per_rank_shape"] = tuple(out2.shape)
+            ret["forked"], ret["unforked"] = outs3[0].clone(), outs3[1].clone()
         lo, hi = sharding.shard_bounds(B, world, rank)
         ret["span%d" % rank] = (lo, hi)
     finally:
@@ -96,3 +105,8 @@ def test_two_rank_run_equals_single_process(B):
     assert ret["per_rank_shape"] == (B, 9, 3, 34)
     assert ret["span0"][1] == ret["span1"][0]
     assert torch.equal(ret["sharded"], want)
+    if B % 2 == 0:
+        h = B // 2
+        assert torch.equal(ret["unforked"][:h], ret["unforked"][h:])          # same seed, same cond: identical shards
+        assert not torch.equal(ret["forked"][:h], ret["forked"][h:])          # rank 1 moved to its own stream
+        assert torch.equal(ret["forked"][:h], ret["unforked"][:h])            # rank 0 keeps the caller's seed
