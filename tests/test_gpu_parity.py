@@ -366,9 +366,15 @@ def test_full_size_properties_b512(impl):
         outs[s] = eng.cfg_forward(x[di], t4, e_c[di], e_u[di], torch.full((4,), s, device=DEV))
     oc, _, _ = eng.model_forward(x[di], t4, False, e_c[di])
     ou, _, _ = eng.model_forward(x[di], t4, True, e_u[di])
-    _close(outs[0.0], ou, rtol=1e-5, atol=1e-5)
-    _close(outs[1.0], oc, rtol=1e-4, atol=1e-4)
-    _close(outs[2.0], ou + 2 * (oc - ou), rtol=1e-4, atol=1e-4)
+    # simt: both sides are the fp32 denoiser; auto: ls_cfg_forward is the bf16x3 tensor-core kernel, ls_model_forward the
+    # fp32 one, so the comparison carries the parity tolerance
+    tol = dict(rtol=1e-5, atol=1e-5) if impl == "simt" else dict(rtol=RTOL, atol=ATOL)
+    tol2 = dict(rtol=1e-4, atol=1e-4) if impl == "simt" else dict(rtol=RTOL, atol=2 * ATOL)
+    _close(outs[0.0], ou, **tol)
+    _close(outs[1.0], oc, **tol2)
+    _close(outs[2.0], ou + 2 * (oc - ou), **tol2)
+    # guidance is linear in the scale inside one implementation, whatever its operand precision
+    _close(outs[2.0], outs[0.0] + 2 * (outs[1.0] - outs[0.0]), rtol=1e-4, atol=1e-4)
 
 
 @pytest.mark.parametrize("impl,B,K", [("auto", 3, 5), ("auto", 300, 7), ("auto", 512, 16), ("simt", 5, 3)])
