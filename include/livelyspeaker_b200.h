@@ -225,6 +225,27 @@ int ls_randn_torch_compat(int32_t n, float* const* outs, const int64_t* numels, 
                           uint64_t philox_offset, uint64_t* total_increment, int32_t device,
                           void* stream);
 
+/* ---- post-sampling rhythm metric --------------------------------------
+ * scripts/test_RAG_ted.py:84-111: the sampler output [B, njoints*3, F] (device) -> per-frame angle change of the listed
+ * joint pairs (angle_diff [B,F], column 0 = 0) and the motion-beat mask (beat_mask [B,F] bytes: frame t in [2, F-1) is a
+ * beat when angle_diff has a strict local minimum there whose drop from either neighbour is >= thres).
+ * mean_dir_vec / angle_pairs ([n_pairs][2] joint indices) / change_angle are HOST arrays (the script's constants).
+ * Stateless like ls_sag_decode; errors through ls_last_error(NULL).                                          */
+#define LS_METRIC_MAX_JOINTS 64
+#define LS_METRIC_MAX_PAIRS 8
+int ls_motion_beats(int32_t B, int32_t njoints, int32_t n_frames, const float* sample,
+                    const float* mean_dir_vec_host, const int32_t* angle_pairs_host,
+                    const float* change_angle_host, int32_t n_pairs, float thres, float* angle_diff,
+                    uint8_t* beat_mask, int32_t device, void* stream);
+/* scripts/test_RAG_ted.py:112-123: per clip, sum over its audio onsets (audio_beats [B,M] seconds, n_audio [B], device)
+ * of exp(-min_t (onset - t/fps)^2 / (2 sigma^2)) over the motion beats t of beat_mask, in fp64 like the script's numpy
+ * arithmetic; clips without a motion beat score 0 and count no audio onsets (the script's `continue`).  Outputs
+ * clip_score [B] fp64, clip_n_motion [B], clip_n_audio [B] (device); the caller sums them into
+ * beat_align_score_sum / motion_beats_sum / num_beats.  The onset detector itself (librosa) stays with the caller.  */
+int ls_beat_align(int32_t B, int32_t n_frames, const uint8_t* beat_mask, const float* audio_beats,
+                  const int32_t* n_audio, int32_t M, float fps, float sigma, double* clip_score,
+                  int32_t* clip_n_motion, int32_t* clip_n_audio, int32_t device, void* stream);
+
 /* Introspection used by tests / bench: number of kernels launched by this handle
  * since creation, and read-back of the step-invariant buffers.                    */
 int64_t ls_launch_count(const ls_handle* h);
@@ -233,6 +254,12 @@ int64_t ls_launch_count(const ls_handle* h);
 /* Copies min(capacity, n) floats into dst (device memory) and stores n in *n_elems.    */
 int ls_debug_buffer(ls_handle* h, int32_t which, float* dst, int64_t capacity, int64_t* n_elems,
                     void* stream);
+/* Per-layer parity aid for MLPblock / LN_spatial (scripts/model/mlp_module.py:29-35, 67-74): while dst != NULL, every
+ * denoiser launch of this handle (ls_step, ls_step_multi's first step, ls_cfg_forward, ls_model_forward) also stores the
+ * residual stream hidden[b][pass][token][512] (pass 0 = cond, 1 = uncond; S tokens) as it is AFTER MLPblock `layer`
+ * (0-based), or right after the input projection / prefix tokens for layer = -1.  dst (device memory,
+ * B*2*S*512 floats) = NULL switches it off.                                                                        */
+int ls_debug_hidden(ls_handle* h, int32_t layer, float* dst);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,8 @@ from .model_util import create_gaussian_diffusion, create_model_and_diffusion, g
 from .rag import RAG
 from .respace import SpacedDiffusion, space_timesteps
 from .sag import Decoder_TRANSFORMER
+from . import metrics  # noqa: E402,F401
 
 __all__ = ["ClassifierFreeSampleModel", "GaussianDiffusion", "LossType", "ModelMeanType", "ModelVarType",
            "ReplayNoise", "TorchNoise", "create_gaussian_diffusion", "create_model_and_diffusion",
-           "get_model_args", "load_model_wo_clip", "RAG", "SpacedDiffusion", "space_timesteps", "Decoder_TRANSFORMER"]
+           "get_model_args", "load_model_wo_clip", "RAG", "SpacedDiffusion", "space_timesteps", "Decoder_TRANSFORMER", "metrics"]

@@ -20,7 +20,7 @@ IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
            "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
-           "ls_debug_buffer"]
+           "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align"]
 
 
 class LsConfig(ctypes.Structure):
@@ -86,6 +86,11 @@ def load_library():
     lib.ls_launch_count.argtypes = [c_void_p]
     lib.ls_launch_count.restype = c_int64
     lib.ls_debug_buffer.argtypes = [c_void_p, c_int32, c_void_p, c_int64, POINTER(c_int64), c_void_p]
+    lib.ls_debug_hidden.argtypes = [c_void_p, c_int32, c_void_p]
+    lib.ls_motion_beats.argtypes = [c_int32, c_int32, c_int32, c_void_p, POINTER(c_float), POINTER(c_int32),
+                                    POINTER(c_float), c_int32, c_float, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.ls_beat_align.argtypes = [c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p,
+                                  c_void_p, c_void_p, c_int32, c_void_p]
     if lib.ls_abi_version() != 1:
         raise LsError("ABI version mismatch: library %d, binding 1" % lib.ls_abi_version())
     _lib = lib
@@ -246,6 +251,19 @@ class Engine:
         out = torch.empty(n.value, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._check(self.lib.ls_debug_buffer(self.h, which, c_void_p(out.data_ptr()), n.value, byref(n), _stream()))
+        return out
+
+    def debug_hidden(self, layer, B):
+        """Arm ls_debug_hidden: returns the [B,2,S,512] tensor the next denoiser launch fills with the residual stream
+        after MLPblock `layer` (-1: after the input projection).  layer=None disarms."""
+        if layer is None:
+            self._check(self.lib.ls_debug_hidden(self.h, -1, None))
+            self._dbg_keep = None
+            return None
+        S = 34 + self.dims.n_pre_emb
+        out = torch.zeros(B, 2, S, self.dims.latent_dim, dtype=torch.float32, device=self.device)
+        self._check(self.lib.ls_debug_hidden(self.h, int(layer), c_void_p(out.data_ptr())))
+        self._dbg_keep = out
         return out
 
     # ---- compute ----------------------------------------------------------------------

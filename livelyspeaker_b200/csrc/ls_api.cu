@@ -407,6 +407,14 @@ extern "C" int ls_q_sample(ls_handle* h, int64_t n, const float* x0, const float
 
 extern "C" int64_t ls_launch_count(const ls_handle* h) { return h ? h->launches : -1; }
 
+extern "C" int ls_debug_hidden(ls_handle* h, int32_t layer, float* dst) {
+  if (!h) return LS_EINVAL;
+  if (dst && (layer < -1 || layer >= h->cfg.n_layers)) return ls_fail(h, LS_EINVAL, "layer %d outside [-1,%d)", layer, h->cfg.n_layers);
+  h->dbg_h = dst;
+  h->dbg_layer = dst ? layer : -2;
+  return LS_OK;
+}
+
 extern "C" int ls_debug_buffer(ls_handle* h, int32_t which, float* dst, int64_t capacity, int64_t* n_elems,
                                void* stream) {
   if (!h || !n_elems) return LS_EINVAL;

@@ -50,7 +50,8 @@ denoise_simt_kernel(LsWeights w, int JD, int n_layers, int pass_mask, const floa
                     const int64_t* __restrict__ t, int t_uniform, const float* __restrict__ A,
                     const float* __restrict__ P, const float* __restrict__ z_mu, const float* __restrict__ z_lv,
                     const float* __restrict__ emo_tok, const float* __restrict__ eps_c,
-                    const float* __restrict__ eps_u, float* __restrict__ out_c, float* __restrict__ out_u) {
+                    const float* __restrict__ eps_u, float* __restrict__ out_c, float* __restrict__ out_u,
+                    float* __restrict__ dbg_h, int dbg_layer) {
   constexpr int NPRE = S - LS_F;
   extern __shared__ float sm[];
   float* hs = sm;                 // [S][512] residual stream
@@ -88,6 +89,11 @@ denoise_simt_kernel(LsWeights w, int JD, int n_layers, int pass_mask, const floa
   const long long tt = t_uniform >= 0 ? (long long)t_uniform : t[b];
   const float emb = w.emb_table[(size_t)tt * LS_D + c];
   __syncthreads();
+  auto dump_hidden = [&](int l) {       // ls_debug_hidden: [b][pass][token][512]
+    if (dbg_h != nullptr && dbg_layer == l)
+      for (int r = 0; r < S; ++r) dbg_h[(((size_t)b * 2 + (uncond ? 1 : 0)) * S + r) * LS_D + c] = hs[r * LS_D + c];
+  };
+  dump_hidden(-1);
 
   for (int l = 0; l < n_layers; ++l) {
     const LsLayerW L = w.layer[l];
@@ -139,6 +145,7 @@ denoise_simt_kernel(LsWeights w, int JD, int n_layers, int pass_mask, const floa
 #pragma unroll
       for (int r = 0; r < S; ++r) hs[r * LS_D + c] += silu_f(acc[r] + bc);
     }
+    dump_hidden(l);
     __syncthreads();
   }
 
@@ -166,7 +173,8 @@ static int launch_simt(ls_handle* h, int B, const float* x, const int64_t* t, in
   LS_CUDA(h, cudaFuncSetAttribute(denoise_simt_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(B, pass_mask == 3 ? 2 : 1);
   denoise_simt_kernel<S><<<grid, 512, smem, s>>>(h->w, h->JD, h->cfg.n_layers, pass_mask, x, t, t_uniform, h->A, h->P,
-                                                 h->z_mu, h->z_lv, h->emo_tok, eps_c, eps_u, out_c, out_u);
+                                                 h->z_mu, h->z_lv, h->emo_tok, eps_c, eps_u, out_c, out_u, h->dbg_h,
+                                                 h->dbg_layer);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
 }

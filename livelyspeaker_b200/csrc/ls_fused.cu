@@ -144,6 +144,8 @@ struct FusedParams {
   int* flags;              // [B] steps completed per clip in this launch (n_steps > 1)
   const long long* t_dev;  // per-clip ORIGINAL timesteps on the device (ls_cfg_forward, mode 2) or nullptr: sp.t_model
   int max_t;               // rows of the time-embedding table (t_dev values are clamped into it)
+  float* dbg_h;            // ls_debug_hidden: [B][2][S][512] residual stream after layer dbg_layer of step 0, or nullptr
+  int dbg_layer;
   ls_step_params sp[KMAX];
   StepIO io[KMAX];
   long long* timing;       // debug (LS_FUSED_TIMING=1): clock64 stamps of block 0, threads 0 and 511
@@ -796,6 +798,18 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
       }
       ++aphase;
       stamp();   // 1: input projection consumed
+      auto dump_hidden = [&](int l) {     // ls_debug_hidden (parity aid; off in production: one uniform test per layer)
+        if (p.dbg_h != nullptr && p.dbg_layer == l && valid && k == 0) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int j = 0; j < NQ; ++j) {
+              const int n = r0 + j;
+              if (n < R) p.dbg_h[((size_t)b * R + n) * LS_D + c0 + 128 * m] = h[m * NQ + j];
+            }
+        }
+      };
+      dump_hidden(-1);
 
       for (int l = 0; l < p.n_layers; ++l) {
         const LsLayerW L = p.w.layer[l];
@@ -875,6 +889,7 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         }
         ++aphase;
         stamp();   // channel-mix epilogue done
+        dump_hidden(l);
       }
 
       // ---- output head operand: plain hi/lo split of h -------------------------------------
@@ -1169,6 +1184,8 @@ int lsf_steps(ls_handle* h, int B, int n_steps, const ls_step_params* p, const l
   fp.flags = fs->flags;
   fp.t_dev = reinterpret_cast<const long long*>(t_dev);
   fp.max_t = h->cfg.max_timestep;
+  fp.dbg_h = h->dbg_h;
+  fp.dbg_layer = h->dbg_layer;
   for (int k = 0; k < n_steps; ++k) {
     fp.sp[k] = p[k];
     fp.io[k].eps_c = io[k].eps_cond; fp.io[k].eps_u = io[k].eps_uncond; fp.io[k].noise = io[k].noise;

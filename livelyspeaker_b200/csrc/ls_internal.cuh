@@ -77,6 +77,8 @@ struct ls_handle {
   float* w1_t = nullptr;    // time_embed.0.weight^T
   float* w2_t = nullptr;    // time_embed.2.weight^T
   int wav_chunk = 0;
+  float* dbg_h = nullptr;   // ls_debug_hidden target (nullptr = off)
+  int dbg_layer = -2;
   void* fused = nullptr;    // state of the tcgen05 path (ls_fused.cu)
   void* wavtc = nullptr;    // state of the tcgen05 WavEncoder convolutions (ls_wavenc_tc.cu)
 };

@@ -1,0 +1,156 @@
+// Post-sampling rhythm metric of the TED evaluation on the device:
+//   scripts/test_RAG_ted.py:84-111  direction vectors -> joint-pair angles -> per-frame angle change -> motion beats
+//   scripts/test_RAG_ted.py:112-123 beat alignment score against audio onset times
+// Stateless entry points (no ls_handle), fp32 in the reference's op order for the angles, fp64 for the score like the
+// reference's numpy arithmetic.  One CTA per clip: the work is a few hundred flops per clip, the point of having it
+// here is that the sampler's output never leaves the device between the loop and the metric.
+#include <cstring>
+
+#include "ls_internal.cuh"
+
+namespace {
+
+struct BeatParams {
+  int njoints, n_frames, n_pairs;
+  float thres;
+  float mean[LS_METRIC_MAX_JOINTS * 3];
+  int pair[LS_METRIC_MAX_PAIRS][2];
+  float change[LS_METRIC_MAX_PAIRS];
+};
+
+constexpr int MAX_F = 64;
+
+__global__ void __launch_bounds__(MAX_F, 8)
+motion_beats_kernel(const BeatParams p, const float* __restrict__ sample, float* __restrict__ angle_diff,
+                    uint8_t* __restrict__ beat_mask) {
+  __shared__ float ang[LS_METRIC_MAX_PAIRS][MAX_F];
+  __shared__ float diff[MAX_F];
+  const int b = blockIdx.x, f = threadIdx.x, F = p.n_frames;
+  const float* sb = sample + (size_t)b * p.njoints * 3 * F;
+  if (f < F) {
+    for (int q = 0; q < p.n_pairs; ++q) {
+      float v[2][3];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int j = p.pair[q][s];
+        // aligned_motions + mean_dir_vec (:88), F.normalize over the 3 components (:90): x / max(||x||, 1e-12)
+        const float x = __fadd_rn(sb[(size_t)(j * 3 + 0) * F + f], p.mean[j * 3 + 0]);
+        const float y = __fadd_rn(sb[(size_t)(j * 3 + 1) * F + f], p.mean[j * 3 + 1]);
+        const float z = __fadd_rn(sb[(size_t)(j * 3 + 2) * F + f], p.mean[j * 3 + 2]);
+        const float nrm = fmaxf(sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z))), 1e-12f);
+        v[s][0] = __fdiv_rn(x, nrm);
+        v[s][1] = __fdiv_rn(y, nrm);
+        v[s][2] = __fdiv_rn(z, nrm);
+      }
+      float ip = __fadd_rn(__fadd_rn(__fmul_rn(v[0][0], v[1][0]), __fmul_rn(v[0][1], v[1][1])), __fmul_rn(v[0][2], v[1][2]));
+      ip = fminf(fmaxf(ip, -1.f), 1.f);                                     // :97
+      ang[q][f] = __fdiv_rn(acosf(ip), 3.14159265358979323846f);           // :98 (math.pi as an fp32 scalar)
+    }
+  }
+  __syncthreads();
+  if (f < F) {
+    float d = 0.f;                                                          // :104 the prepended zero column
+    if (f >= 1) {
+      for (int q = 0; q < p.n_pairs; ++q) {                                 // :100-103, pairs accumulated in order
+        const float t = __fdiv_rn(__fdiv_rn(fabsf(__fsub_rn(ang[q][f], ang[q][f - 1])), p.change[q]), (float)p.n_pairs);
+        d = (q == 0) ? t : __fadd_rn(d, t);
+      }
+    }
+    diff[f] = d;
+    angle_diff[(size_t)b * F + f] = d;
+  }
+  __syncthreads();
+  if (f < F) {
+    uint8_t m = 0;
+    if (f >= 2 && f < F - 1) {                                              // :107 for t in range(2, 33)
+      const float a = diff[f], lo = diff[f - 1], hi = diff[f + 1];
+      if (a < lo && a < hi && (__fsub_rn(lo, a) >= p.thres || __fsub_rn(hi, a) >= p.thres)) m = 1;
+    }
+    beat_mask[(size_t)b * F + f] = m;
+  }
+}
+
+__global__ void __launch_bounds__(128, 8)
+beat_align_kernel(int F, int M, double fps, double sigma, const uint8_t* __restrict__ beat_mask,
+                  const float* __restrict__ audio_beats, const int* __restrict__ n_audio, double* __restrict__ clip_score,
+                  int* __restrict__ clip_n_motion, int* __restrict__ clip_n_audio) {
+  __shared__ double part[128];
+  __shared__ int n_motion;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const uint8_t* mb = beat_mask + (size_t)b * F;
+  if (tid == 0) {
+    int n = 0;
+    for (int t = 0; t < F; ++t) n += mb[t] ? 1 : 0;
+    n_motion = n;
+  }
+  __syncthreads();
+  const int na = min(max(n_audio[b], 0), M);
+  double s = 0.0;
+  if (n_motion > 0) {
+    for (int i = tid; i < na; i += 128) {
+      const double ab = (double)audio_beats[(size_t)b * M + i];
+      double best = 1e300;
+      for (int t = 0; t < F; ++t)
+        if (mb[t]) {
+          const double d = ab - (double)t / fps;                            // :110 float(t) / 15.0
+          best = fmin(best, d * d);
+        }
+      s += exp(-best / (2.0 * sigma * sigma));                              // :120
+    }
+  }
+  part[tid] = s;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0.0;
+    for (int i = 0; i < 128; ++i) tot += part[i];
+    clip_score[b] = tot;
+    clip_n_motion[b] = n_motion;
+    clip_n_audio[b] = n_motion > 0 ? na : 0;                                // :117-118 clips without motion beats are skipped
+  }
+}
+
+}  // namespace
+
+extern "C" int ls_motion_beats(int32_t B, int32_t njoints, int32_t n_frames, const float* sample,
+                               const float* mean_dir_vec_host, const int32_t* angle_pairs_host,
+                               const float* change_angle_host, int32_t n_pairs, float thres, float* angle_diff,
+                               uint8_t* beat_mask, int32_t device, void* stream) {
+  if (B < 1 || !sample || !mean_dir_vec_host || !angle_pairs_host || !change_angle_host || !angle_diff || !beat_mask)
+    return ls_fail(nullptr, LS_EINVAL, "ls_motion_beats: bad argument");
+  if (njoints < 1 || njoints > LS_METRIC_MAX_JOINTS || n_pairs < 1 || n_pairs > LS_METRIC_MAX_PAIRS || n_frames < 3 ||
+      n_frames > MAX_F)
+    return ls_fail(nullptr, LS_EUNSUPPORTED, "ls_motion_beats: <= %d joints, <= %d pairs, 3..%d frames", LS_METRIC_MAX_JOINTS,
+                   LS_METRIC_MAX_PAIRS, MAX_F);
+  BeatParams p{};
+  p.njoints = njoints;
+  p.n_frames = n_frames;
+  p.n_pairs = n_pairs;
+  p.thres = thres;
+  memcpy(p.mean, mean_dir_vec_host, sizeof(float) * njoints * 3);
+  for (int q = 0; q < n_pairs; ++q) {
+    p.pair[q][0] = angle_pairs_host[2 * q];
+    p.pair[q][1] = angle_pairs_host[2 * q + 1];
+    if (p.pair[q][0] < 0 || p.pair[q][0] >= njoints || p.pair[q][1] < 0 || p.pair[q][1] >= njoints)
+      return ls_fail(nullptr, LS_EINVAL, "ls_motion_beats: joint index out of range in pair %d", q);
+    p.change[q] = change_angle_host[q];
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_motion_beats: cudaSetDevice(%d)", device);
+  motion_beats_kernel<<<B, MAX_F, 0, (cudaStream_t)stream>>>(p, sample, angle_diff, beat_mask);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_motion_beats: %s", cudaGetErrorString(e));
+  return LS_OK;
+}
+
+extern "C" int ls_beat_align(int32_t B, int32_t n_frames, const uint8_t* beat_mask, const float* audio_beats,
+                             const int32_t* n_audio, int32_t M, float fps, float sigma, double* clip_score,
+                             int32_t* clip_n_motion, int32_t* clip_n_audio, int32_t device, void* stream) {
+  if (B < 1 || n_frames < 1 || M < 1 || !beat_mask || !audio_beats || !n_audio || !clip_score || !clip_n_motion ||
+      !clip_n_audio || !(fps > 0.f) || !(sigma > 0.f))
+    return ls_fail(nullptr, LS_EINVAL, "ls_beat_align: bad argument");
+  if (cudaSetDevice(device) != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_beat_align: cudaSetDevice(%d)", device);
+  beat_align_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(n_frames, M, (double)fps, (double)sigma, beat_mask, audio_beats,
+                                                          n_audio, clip_score, clip_n_motion, clip_n_audio);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_beat_align: %s", cudaGetErrorString(e));
+  return LS_OK;
+}

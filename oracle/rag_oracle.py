@@ -71,15 +71,19 @@ def n_layers(sd):
     return n
 
 
-def trans_mlp(sd, x, t):
-    """mlp_module.py:85-91."""
+def trans_mlp(sd, x, t, trace=None):
+    """mlp_module.py:85-91.  `trace` (a list) receives the hidden state before the first block and after every block."""
     emb = timestep_embed(sd, t)
+    if trace is not None:
+        trace.append(x)
     for layer in range(n_layers(sd)):
         x = mlp_block(sd, layer, x, emb)
+        if trace is not None:
+            trace.append(x)
     return x
 
 
-def rag_forward(sd, x, t, y, style_eps, njoints, nfeats):
+def rag_forward(sd, x, t, y, style_eps, njoints, nfeats, trace=None):
     """RAG.py:98-133 (TED) / scripts_beat/model/RAG.py:101-137 (BEAT, selected by
     the presence of 'emotion_embedding.weight').  style_eps replaces the
     randn_like of reparameterize (RAG.py:10-13).  Mutates y['origin_x'] in place
@@ -105,7 +109,7 @@ def rag_forward(sd, x, t, y, style_eps, njoints, nfeats):
         toks.append(sd["emotion_embedding.weight"][y["emo"][:, 0]][:, None])
     n_pre = len(toks)
     h = torch.cat(toks + [h], dim=1)
-    h = trans_mlp(sd, h, t)[:, n_pre:].permute(1, 0, 2)
+    h = trans_mlp(sd, h, t, trace)[:, n_pre:].permute(1, 0, 2)
     o = F.linear(h, sd["output_process.poseFinal.weight"], sd["output_process.poseFinal.bias"])
     o = o.reshape(nframes, bs, njoints, nfeats).permute(1, 2, 3, 0)
     return {"output": o, "z_mu": z_mu, "z_logvar": z_lv}

@@ -56,3 +56,8 @@ def golden_schedule():
 def golden_hooks():
     return {"ted": dict(np.load(os.path.join(GOLDEN, "hooks_ted.npz"))),
             "beat": dict(np.load(os.path.join(GOLDEN, "hooks_beat.npz")))}
+
+
+@pytest.fixture(scope="session")
+def golden_metrics():
+    return dict(np.load(os.path.join(GOLDEN, "metrics.npz")))

@@ -700,3 +700,83 @@ def test_input_validation():
         eng.cfg_forward(x, torch.tensor([5, 1000], device=DEV), z, z, y["scale"])
     with pytest.raises(IndexError):
         eng.model_forward(x, torch.tensor([-1, 3], device=DEV), False, z)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_per_layer_hidden_states_vs_oracle(name, impl):
+    """MLPblock / LN_spatial in isolation: the residual stream of BOTH kernels after the input
+    projection and after MLPblocks 0, 3 and 7 (ls_debug_hidden) against the oracle's per-layer states - the oracle's
+    LN_spatial / MLPblock / TransMLP are pinned to the reference by the ln_out / block_out / backbone_out fixtures."""
+    dims, sd, cfg, diffusion = build(name, "", impl=impl)
+    B, i = 2, 640
+    S = 34 + dims.n_pre_emb
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(B, dims.njoints, dims.nfeats, 34, generator=g)
+    e_c, e_u = torch.randn(B, 1, 512, generator=g), torch.randn(B, 1, 512, generator=g)
+    nz = torch.randn(B, dims.njoints, dims.nfeats, 34, generator=g)
+    t = torch.full((B,), i, dtype=torch.long)
+    traces = []
+    with torch.no_grad():
+        for unc, eps in ((False, e_c), (True, e_u)):
+            yc = synthetic.synth_cond(dims, B)
+            if unc:
+                yc["uncond"] = True
+            tr = []
+            rag_oracle.rag_forward(sd, x, t, yc, eps, dims.njoints, dims.nfeats, trace=tr)
+            traces.append(tr)
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    eng = cfg.model.engine(B)
+    eng.set_cond(y, force=True)
+    p = diffusion.step_params(i, ddim=False, clip_denoised=False)
+    xd = x.to(DEV)
+    worst = 0.0
+    try:
+        for layer in (-1, 0, 3, 7):
+            hid = eng.debug_hidden(layer, B)
+            eng.step(p, xd, e_c.to(DEV), e_u.to(DEV), nz.to(DEV), y["scale"], torch.empty_like(xd), None)
+            torch.cuda.synchronize()
+            assert hid.shape == (B, 2, S, 512)
+            for ps in (0, 1):
+                want = traces[ps][layer + 1]
+                worst = max(worst, _maxerr(hid[:, ps], want))
+                _close(hid[:, ps], want)
+    finally:
+        eng.debug_hidden(None, B)
+    print("per-layer hidden states (%s, %s): max |gpu - oracle| = %.3g" % (name, impl, worst))
+
+
+def test_rhythm_metric_on_device(golden_metrics):
+    """ls_motion_beats / ls_beat_align against the fixture made by the reference's own lines
+    (scripts/test_RAG_ted.py:84-123) and the oracle; then on a real sampler output at B=64."""
+    from livelyspeaker_b200 import metrics
+    from oracle import metrics_oracle
+    g = golden_metrics
+    sample = torch.from_numpy(g["sample"]).to(DEV)
+    angle_diff, mask = metrics.motion_beats(sample)
+    # |angle change| / 0.0035 / 4 amplifies the 1-2 ulp acosf / dot-product differences between devices by ~71x
+    np.testing.assert_allclose(angle_diff.cpu().numpy(), g["angle_diff"], rtol=1e-4, atol=2e-4)
+    got, want = mask.cpu().numpy(), g["beat_mask"]
+    ad = g["angle_diff"]
+    for b, t in zip(*np.nonzero(got != want)):      # a flipped decision is legitimate only on a knife edge
+        margins = [ad[b, t - 1] - ad[b, t], ad[b, t + 1] - ad[b, t]]
+        edge = min(abs(m) for m in margins + [margins[0] - float(g["thres"]), margins[1] - float(g["thres"])])
+        assert edge < 5e-4, "beat decision differs at clip %d frame %d with margin %.3g" % (b, t, edge)
+    assert (got != want).sum() <= 2
+    beats = [list(g["audio_beats"][b, :g["audio_n"][b]]) for b in range(sample.shape[0])]
+    s = metrics.beat_align_score(torch.from_numpy(want).to(DEV), beats)
+    np.testing.assert_allclose(s["clip_score"].cpu().numpy(), g["clip_score"], rtol=1e-6, atol=1e-7)
+    assert s["num_beats"] == int(g["total_audio"]) and s["motion_beats_sum"] == int(g["total_motion"])
+    assert abs(s["beat_align_score_sum"] - float(g["total_score"])) < 1e-5
+    # end of the drop-in flow: sampler output -> metric, all on the device
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    B = 64
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    torch.manual_seed(3)
+    out = diffusion.ddim_sample_loop(cfg, (B, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=90)
+    ad_dev, mask_dev = metrics.motion_beats(out)
+    o = metrics_oracle.motion_beats(out.cpu(), metrics.MEAN_DIR_VEC, metrics.ANGLE_PAIR, metrics.CHANGE_ANGLE, metrics.THRES)
+    np.testing.assert_allclose(ad_dev.cpu().numpy(), o["angle_diff"].numpy(), rtol=1e-4, atol=5e-4)
+    assert (mask_dev.cpu() != o["beat_mask"]).sum() <= max(2, int(0.01 * o["beat_mask"].sum()))
+    with pytest.raises(ls.LsError):
+        metrics.motion_beats(out.cpu())

@@ -184,3 +184,13 @@ def test_product_never_imports_oracle_or_reference():
                 assert not pat.search(src), "%s references oracle/ or the reference tree" % f
     bench = open(os.path.join(ROOT, "bench.py")).read() if os.path.exists(os.path.join(ROOT, "bench.py")) else ""
     assert "/root/reference" not in bench
+
+
+def test_metrics_have_no_cpu_path():
+    """The rhythm metric mirrors scripts/test_RAG_ted.py:84-123 on the device only: host tensors raise."""
+    from livelyspeaker_b200 import metrics
+    from livelyspeaker_b200._cabi import LsError
+    with pytest.raises(LsError):
+        metrics.motion_beats(torch.zeros(2, 9, 3, 34))
+    with pytest.raises(LsError):
+        metrics.beat_align_score(torch.zeros(2, 34, dtype=torch.uint8), [[0.1], []])

@@ -239,3 +239,22 @@ def test_hooked_loops(name, tag, golden_hooks):
     sd = synthetic.synth_state_dict(dims, seed=1)
     out, _ = run_oracle_hooks(name, tag, dims, sd)
     _close(out, golden_hooks[name]["loop_" + tag])
+
+
+def test_rhythm_metric_oracle(golden_metrics):
+    """oracle/metrics_oracle.py against the fixture the reference's own lines produced (scripts/test_RAG_ted.py:84-123
+    executed by tests/golden/make_golden_metrics.py): angle changes, motion-beat masks, per-clip and total scores."""
+    from oracle import metrics_oracle
+    g = golden_metrics
+    o = metrics_oracle.motion_beats(torch.from_numpy(g["sample"]), g["mean_dir_vec"], g["angle_pair"], g["change_angle"],
+                                    float(g["thres"]))
+    np.testing.assert_allclose(o["angle_diff"].numpy(), g["angle_diff"], rtol=0, atol=1e-6)
+    assert (o["beat_mask"].numpy() == g["beat_mask"]).all() and int(g["beat_mask"].sum()) == int(g["total_motion"])
+    beats = [list(g["audio_beats"][b, :g["audio_n"][b]].astype(np.float64)) for b in range(g["sample"].shape[0])]
+    s = metrics_oracle.beat_align(o["beat_mask"], beats, float(g["sigma"]))
+    np.testing.assert_allclose(s["clip_score"], g["clip_score"], rtol=1e-6, atol=1e-7)      # onsets stored as fp32
+    assert s["total_audio"] == int(g["total_audio"]) and s["total_motion"] == int(g["total_motion"])
+    from livelyspeaker_b200 import metrics
+    assert list(g["mean_dir_vec"]) == metrics.MEAN_DIR_VEC and [tuple(p) for p in g["angle_pair"]] == metrics.ANGLE_PAIR
+    assert list(g["change_angle"]) == metrics.CHANGE_ANGLE and float(g["thres"]) == metrics.THRES
+    assert float(g["sigma"]) == metrics.SIGMA
