@@ -163,6 +163,22 @@ __device__ __forceinline__ float silu_fast(float z) {
   return z * r;
 }
 
+// (h0, h1) += silu(z0), silu(z1): FMUL2, 2 x EX2, FADD2, 2 x RCP, FFMA2 - 7 instructions for two activations
+__device__ __forceinline__ void silu_acc2(float& h0, float& h1, f32x2 z) {
+  float t0, t1, e0, e1, d0, d1, r0, r1;
+  upk2(mul2(z, bc2(-1.4426950408889634f)), t0, t1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(t0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(t1));
+  upk2(add2(pk2(e0, e1), bc2(1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  upk2(fma2(z, pk2(r0, r1), pk2(h0, h1)), h0, h1);
+}
+
+// Per-row statistics live in shared memory in PAIR layout: rows (2i, 2i+1) share one float4 = (x_2i, x_2i+1, y_2i,
+// y_2i+1), so that one 128-bit load hands a thread the packed operands of both rows of a register pair.
+__device__ __forceinline__ int pair_slot(int row) { return ((row >> 1) << 2) + (row & 1); }
+
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -224,34 +240,42 @@ __device__ __forceinline__ void butterfly(float* v, int lane) {
 
 // Per-row (sum, sum of squares) over the 512 channels of this group's 18 rows.  `shift` = the previous mean of
 // the row (robust single-pass variance), or 0 when use_shift is false.
-//   CORR == 0: stats[row] = (rstd, -mean * rstd) (normalisation is one FMA), means[row] = mean.
+//   CORR == 0: stats[row] = (rstd, -mean * rstd) (normalisation is one FMA; pair layout), means[row] = mean.
 //   CORR == 1: (m, s) = the mean / rstd the operand tile was normalised with; the exact (mu, rho)
 //              give the channel-mix epilogue's gd[row] = (rho / s, (m - mu) * rho) and replace stats / means.
 template <int CORR>
 __device__ __forceinline__ void ln_stats_q(const float (&h)[72], uint8_t* sm, int rq, bool use_shift) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float* part = reinterpret_cast<float*>(sm + OFF_PART);          // [16 warps][18 rows][2]
-  float2* stats = reinterpret_cast<float2*>(sm + OFF_STATS);
+  float* stats = reinterpret_cast<float*>(sm + OFF_STATS);        // pair layout (rstd, -mean * rstd)
   float* means = reinterpret_cast<float*>(sm + OFF_MEAN);
   const int r0 = NQ * rq;
-  auto row_sq = [&](int j, float& s, float& q) {
-    const float sh = use_shift ? means[r0 + j] : 0.f;
-    const float d0 = h[j] - sh, d1 = h[NQ + j] - sh, d2 = h[2 * NQ + j] - sh, d3 = h[3 * NQ + j] - sh;
-    s = (d0 + d1) + (d2 + d3);
-    q = fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+  // rows j, j+1 (a register pair of every M-tile) at once: packed (sum, sum of squares) over the 4 channels
+  auto row_sq2 = [&](int j, float& s0, float& s1, float& q0, float& q1) {
+    f32x2 d0 = pk2(h[j], h[j + 1]), d1 = pk2(h[NQ + j], h[NQ + j + 1]), d2 = pk2(h[2 * NQ + j], h[2 * NQ + j + 1]),
+          d3 = pk2(h[3 * NQ + j], h[3 * NQ + j + 1]);
+    if (use_shift) {
+      const float2 m2 = *reinterpret_cast<const float2*>(means + r0 + j);
+      const f32x2 sh = pk2(m2.x, m2.y);
+      d0 = sub2(d0, sh);
+      d1 = sub2(d1, sh);
+      d2 = sub2(d2, sh);
+      d3 = sub2(d3, sh);
+    }
+    upk2(add2(add2(d0, d1), add2(d2, d3)), s0, s1);
+    upk2(add2(fma2(d0, d0, mul2(d1, d1)), fma2(d2, d2, mul2(d3, d3))), q0, q1);
   };
 #pragma unroll
   for (int g = 0; g < 2; ++g) {          // rows 8g .. 8g+7: values 0..7 = sums, 8..15 = sums of squares
     float v[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) row_sq(8 * g + i, v[i], v[8 + i]);
+    for (int i = 0; i < 8; i += 2) row_sq2(8 * g + i, v[i], v[i + 1], v[8 + i], v[9 + i]);
     butterfly<16>(v, lane);              // lane bits (4 | 3,2,1) select (q? | row)
     if ((lane & 1) == 0) part[((warp * NQ) + 8 * g + ((lane >> 1) & 7)) * 2 + (lane >> 4)] = v[0];
   }
   {                                      // rows 16, 17
     float v[4];
-    row_sq(16, v[0], v[2]);
-    row_sq(17, v[1], v[3]);
+    row_sq2(16, v[0], v[1], v[2], v[3]);
     butterfly<4>(v, lane);               // lane bits (4 | 3) select (q? | row)
     if ((lane & 7) == 0) part[((warp * NQ) + 16 + ((lane >> 3) & 1)) * 2 + (lane >> 4)] = v[0];
   }
@@ -265,16 +289,19 @@ __device__ __forceinline__ void ln_stats_q(const float (&h)[72], uint8_t* sm, in
       ss += pr.x;
       qq += pr.y;
     }
-    const float old_mean = means[r0 + j], old_rstd = stats[r0 + j].x;
+    const int ps = pair_slot(r0 + j);
+    const float old_mean = means[r0 + j], old_rstd = stats[ps];
     const float sh = use_shift ? old_mean : 0.f;
     const float md = ss * (1.f / 512.f);
     const float var = fmaxf(qq * (1.f / 512.f) - md * md, 0.f);
     const float mu = sh + md, rho = rsqrtf(var + 1e-5f);
     if (CORR) {
-      float2* gd = reinterpret_cast<float2*>(sm + OFF_GD);
-      gd[r0 + j] = make_float2(__fdividef(rho, old_rstd), (old_mean - mu) * rho);
+      float* gd = reinterpret_cast<float*>(sm + OFF_GD);           // pair layout (row scale, row shift)
+      gd[ps] = __fdividef(rho, old_rstd);
+      gd[ps + 2] = (old_mean - mu) * rho;
     }
-    stats[r0 + j] = make_float2(rho, -mu * rho);
+    stats[ps] = rho;
+    stats[ps + 2] = -mu * rho;
     means[r0 + j] = mu;
   }
   group_bar(rq);
@@ -305,7 +332,8 @@ __device__ __forceinline__ void store_pair(uint32_t addr, bool odd, float u0, fl
   const uint32_t hb = *reinterpret_cast<const uint32_t*>(&hi);
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr + HI_OFF), "r"(hb));
   if (PRECISE) {
-    const float r0 = lo_ch - __uint_as_float(hb << 16), r1 = hi_ch - __uint_as_float(hb & 0xFFFF0000u);
+    float r0, r1;
+    upk2(sub2(pk2(lo_ch, hi_ch), pk2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xFFFF0000u))), r0, r1);
     const __nv_bfloat162 lo = __floats2bfloat162_rn(r0, r1);
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&lo)));
   }
@@ -318,23 +346,29 @@ struct RowBases { uint32_t ya0, ya2, ytail; };
 template <bool PRECISE, int MODE>
 __device__ __forceinline__ void store_rows(const float* hm, const float2* st, uint32_t u_s, const RowBases& rb,
                                            uint32_t ch_off, bool odd, bool ok_tail) {
-  auto norm = [&](float v, float rstd, float nmr) { return MODE == 2 ? v : fmaf(v, rstd, nmr); };
+  // rows j, j+1 normalised as one packed FMA; st + j = (rstd_j, rstd_j+1, -mean*rstd_j, -mean*rstd_j+1) (pair layout)
+  auto norm2 = [&](int j, float& n0, float& n1) {
+    if (MODE == 2) {
+      n0 = hm[j];
+      n1 = hm[j + 1];
+    } else {
+      const float4 s4 = *reinterpret_cast<const float4*>(st + j);
+      upk2(fma2(pk2(hm[j], hm[j + 1]), pk2(s4.x, s4.y), pk2(s4.z, s4.w)), n0, n1);
+    }
+  };
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
     if ((j & 4) != 0) continue;              // j = 0, 2, 8, 10: row pairs (j, j+4) and (j+1, j+5)
-    float4 sa = make_float4(1.f, 0.f, 1.f, 0.f), sb = sa;
-    if (MODE != 2) {
-      sa = *reinterpret_cast<const float4*>(st + j);          // (rstd, -mean*rstd) of rows j, j+1
-      sb = *reinterpret_cast<const float4*>(st + j + 4);      // ... of rows j+4, j+5
-    }
-    store_pair<PRECISE>(u_s + row_addr(rb.ya0, rb.ya2, j) + ch_off, odd, norm(hm[j], sa.x, sa.y), norm(hm[j + 4], sb.x, sb.y));
-    store_pair<PRECISE>(u_s + row_addr(rb.ya0, rb.ya2, j + 1) + ch_off, odd, norm(hm[j + 1], sa.z, sa.w),
-                        norm(hm[j + 5], sb.z, sb.w));
+    float a0, a1, b0, b1;
+    norm2(j, a0, a1);
+    norm2(j + 4, b0, b1);
+    store_pair<PRECISE>(u_s + row_addr(rb.ya0, rb.ya2, j) + ch_off, odd, a0, b0);
+    store_pair<PRECISE>(u_s + row_addr(rb.ya0, rb.ya2, j + 1) + ch_off, odd, a1, b1);
   }
   if (ok_tail) {                             // warp-uniform; rows 16, 17
-    float4 sa = make_float4(1.f, 0.f, 1.f, 0.f);
-    if (MODE != 2) sa = *reinterpret_cast<const float4*>(st + 16);
-    store_pair<PRECISE>(u_s + rb.ytail + ch_off, odd, norm(hm[16], sa.x, sa.y), norm(hm[17], sa.z, sa.w));
+    float a0, a1;
+    norm2(16, a0, a1);
+    store_pair<PRECISE>(u_s + rb.ytail + ch_off, odd, a0, a1);
   }
 }
 
@@ -349,13 +383,17 @@ __device__ __forceinline__ void store_a_tok(const float* hm, const float2* st, f
   uint32_t hi[9], lo[9];
 #pragma unroll
   for (int j = 0; j < NQ; j += 2) {
-    const float4 s4 = *reinterpret_cast<const float4*>(st + j);        // (rstd, -mean*rstd) of rows j, j+1
-    const float u0 = fmaf(fmaf(hm[j], s4.x, s4.y), ab.x, ab.y), u1 = fmaf(fmaf(hm[j + 1], s4.z, s4.w), ab.x, ab.y);
+    const float4 s4 = *reinterpret_cast<const float4*>(st + j);        // pair layout: (rstd_j, rstd_j+1, nmr_j, nmr_j+1)
+    const f32x2 u = fma2(fma2(pk2(hm[j], hm[j + 1]), pk2(s4.x, s4.y), pk2(s4.z, s4.w)), bc2(ab.x), bc2(ab.y));
+    float u0, u1;
+    upk2(u, u0, u1);
     const __nv_bfloat162 h2 = __floats2bfloat162_rn(u0, u1);           // low half = row j (k even)
     const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h2);
     hi[j >> 1] = hb;
     if (PRECISE) {
-      const __nv_bfloat162 l2 = __floats2bfloat162_rn(u0 - __uint_as_float(hb << 16), u1 - __uint_as_float(hb & 0xFFFF0000u));
+      float l0, l1;
+      upk2(sub2(u, pk2(__uint_as_float(hb << 16), __uint_as_float(hb & 0xFFFF0000u))), l0, l1);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(l0, l1);
       lo[j >> 1] = *reinterpret_cast<const uint32_t*>(&l2);
     }
   }
@@ -380,35 +418,38 @@ __device__ __forceinline__ void store_a_tok(const float* hm, const float2* st, f
 // This thread's 18 columns [taddr, taddr + 18) of one accumulator (CAT: plus the columns 72 further that hold
 // the other partial product) handed to f(j, value) with compile-time j.  Whole warps only.
 template <bool CAT, class F>
-__device__ __forceinline__ void acc_rows(uint32_t taddr, F&& f) {     // f(j, v_j, v_j+1), j even
+__device__ __forceinline__ void acc_rows(uint32_t taddr, F&& f) {     // f(j, packed (v_j, v_j+1)), j even
 #pragma unroll
   for (int c0 = 0; c0 < 16; c0 += 8) {
     float a[8], b[8];
     if (CAT) {
       tmem_ld8x2(taddr + c0, taddr + CAT_HI + c0, a, b);
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) f(c0 + i, add2(pk2(a[i], a[i + 1]), pk2(b[i], b[i + 1])));
     } else {
       tmem_ld8(taddr + c0, a);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) b[i] = 0.f;
+      for (int i = 0; i < 8; i += 2) f(c0 + i, pk2(a[i], a[i + 1]));
     }
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) f(c0 + i, a[i] + b[i], a[i + 1] + b[i + 1]);
   }
-  float a[2], b[2] = {0.f, 0.f};
-  if (CAT) tmem_ld2x2(taddr + 16, taddr + CAT_HI + 16, a, b);
-  else tmem_ld2(taddr + 16, a);
-  f(16, a[0] + b[0], a[1] + b[1]);
+  float a[2], b[2];
+  if (CAT) {
+    tmem_ld2x2(taddr + 16, taddr + CAT_HI + 16, a, b);
+    f(16, add2(pk2(a[0], a[1]), pk2(b[0], b[1])));
+  } else {
+    tmem_ld2(taddr + 16, a);
+    f(16, pk2(a[0], a[1]));
+  }
 }
 
 // Token-mix accumulator: the 18 columns in ONE load round (16 + 2, a single wait).
 template <class F>
-__device__ __forceinline__ void acc_rows_tok(uint32_t taddr, F&& f) {
+__device__ __forceinline__ void acc_rows_tok(uint32_t taddr, F&& f) {  // f(j, packed (v_j, v_j+1)), j even
   float a[16], b[2];
   tmem_ld16p2(taddr, a, b);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) f(i, a[i]);
-  f(16, b[0]);
-  f(17, b[1]);
+  for (int i = 0; i < 16; i += 2) f(i, pk2(a[i], a[i + 1]));
+  f(16, pk2(b[0], b[1]));
 }
 
 // The head reads whole accumulator rows (lane = output feature): columns [0, R) of a channel-type buffer.
@@ -798,7 +839,9 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
       for (int m = 0; m < 4; ++m) {
         wait_acc(m);
         acc_rows<PRECISE>(lane_base + (uint32_t)((m & 1) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
-                          [&](int j, float v0, float v1) {
+                          [&](int j, f32x2 v) {
+          float v0, v1;
+          upk2(v, v0, v1);
           const int n = r0 + j, tok = n >= S ? n - S : n, n1 = n + 1, tok1 = n1 >= S ? n1 - S : n1;
           if (tok >= NPRE && n < R) h[m * NQ + j] += v0;         // prefix-token rows keep their direct values
           if (tok1 >= NPRE && n1 < R) h[m * NQ + j + 1] += v1;
@@ -826,9 +869,9 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         // x = x + emb ; LN1 ; -> operand tile
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          const float emb = emb_s[c0 + 128 * m];
+          const f32x2 emb = bc2(emb_s[c0 + 128 * m]);
 #pragma unroll
-          for (int j = 0; j < NQ; ++j) h[m * NQ + j] += emb;
+          for (int j = 0; j < NQ; j += 2) upk2(add2(pk2(h[m * NQ + j], h[m * NQ + j + 1]), emb), h[m * NQ + j], h[m * NQ + j + 1]);
         }
         if (l == 0) ln_stats_q<0>(h, sm, rq, false);     // provisional means for the shift
         ln_stats_q<0>(h, sm, rq, true);
@@ -852,8 +895,12 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         for (int m = 0; m < 4; ++m) {
           wait_acc(m);                  // accumulator m complete => operand buffer m & 1 is free again
           if (m + 2 < 4) a_tok(m + 2);
-          acc_rows_tok(lane_base + (uint32_t)(TOK_D0 + (m & 1) * NROW + r0), [&](int j, float v) {
-            if (j < 16 || ok_tail) h[m * NQ + j] += silu_fast(TokBias<S>::kInGemm ? v : v + btok_s[r0 + j]);
+          acc_rows_tok(lane_base + (uint32_t)(TOK_D0 + (m & 1) * NROW + r0), [&](int j, f32x2 v) {
+            if (!TokBias<S>::kInGemm) {
+              const float2 b2 = *reinterpret_cast<const float2*>(btok_s + r0 + j);
+              v = add2(v, pk2(b2.x, b2.y));
+            }
+            if (j < 16 || ok_tail) silu_acc2(h[m * NQ + j], h[m * NQ + j + 1], v);
           });
           if (m < 2) drained(BAR_TDRAIN0 + m);
           store_rows<PRECISE, 1>(h + m * NQ, stats_q, u_s, rb, (uint32_t)(2 * m) * CBS, odd, ok_tail);
@@ -886,12 +933,10 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
           const float Sc = sct.x, tc = sct.y;
           if (m == 0) stamp();   // first channel-mix accumulator ready
           acc_rows<PRECISE>(lane_base + (uint32_t)((m & 1) * ACC_COLS + r0) + (PRECISE ? 0u : (uint32_t)CAT_HI),
-                            [&](int j, float v0, float v1) {
-            const float4 r = *reinterpret_cast<const float4*>(gd_q + j);     // (scale, shift) of rows j, j+1
-            if (j < 16 || ok_tail) {
-              h[m * NQ + j] += silu_fast(fmaf(r.x, v0, fmaf(r.y, Sc, tc)));
-              h[m * NQ + j + 1] += silu_fast(fmaf(r.z, v1, fmaf(r.w, Sc, tc)));
-            }
+                            [&](int j, f32x2 v) {
+            const float4 r = *reinterpret_cast<const float4*>(gd_q + j);     // pair layout: (scale_j, scale_j+1, shift_j, shift_j+1)
+            if (j < 16 || ok_tail)
+              silu_acc2(h[m * NQ + j], h[m * NQ + j + 1], fma2(pk2(r.x, r.y), v, fma2(pk2(r.z, r.w), bc2(Sc), bc2(tc))));
           });
           if (m < 2) drained(BAR_DRAIN0 + m);
           if (m == 2) stamp();   // three of four M-tiles consumed

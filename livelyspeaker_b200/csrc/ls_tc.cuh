@@ -317,6 +317,40 @@ __device__ __forceinline__ void umma_commit_mc_s_elect(uint32_t bar_s, uint16_t 
       : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (sm_100a: FADD2 / FMUL2 / FFMA2) ------------------------------------------------
+// One instruction, two IEEE fp32 results (each identical to the scalar op): the epilogue warps of the fused kernel are
+// issue-bound, so pairing rows (j, j+1) of a thread's residual stream halves their fp32 issue slots.  ptxas keeps a
+// pair in an aligned register pair (the mov.b64 pack / unpack below then costs nothing) and takes a scalar broadcast
+// ({a, a}) as a plain register operand.
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 bc2(float a) { return pk2(a, a); }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 // ---- cta_group::2 (CTA pair) forms: issued by the LEADER CTA (cluster rank 0) only; M = 256 = 128 rows of A from
 // each CTA's shared memory at the same offset, N/2 rows of B from each CTA, every CTA's tensor memory receives its
 // 128 rows of D for all N columns (validated by umma_probe2.cu).
