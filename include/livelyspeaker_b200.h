@@ -213,6 +213,17 @@ typedef struct ls_sag_weights {
  * may be NULL) -> out [B,J*D,F].  Errors: ls_last_error(NULL).                           */
 int ls_sag_decode(const ls_sag_weights* w, int32_t B, const float* x, const float* z,
                   const uint8_t* mask, float* out, void* stream);
+/* The same decoder on the tensor cores (tcgen05, bf16x3 split operands, fp32 accumulation; self-attention, softmax,
+ * LayerNorm and GELU in fp32): ls_sag_create builds the weight tapes from *w (the pointed-to weights must stay valid
+ * only during the call; biases / LayerNorm vectors / mapping / finallayer / pe / cross-attention matrices are read by
+ * every decode and must stay valid for the handle's life) and the workspaces for max_batch clips (557 KB per clip);
+ * ls_sag_decode_tc has ls_sag_decode's contract.  ls_sag_decode stays the exact-order fp32 cross-check.              */
+typedef struct ls_sag ls_sag;
+int ls_sag_create(ls_sag** out, const ls_sag_weights* w, int32_t max_batch, int32_t device, void* stream);
+int ls_sag_decode_tc(ls_sag* s, int32_t B, const float* x, const float* z, const uint8_t* mask,
+                     float* out, void* stream);
+int64_t ls_sag_launch_count(const ls_sag* s);
+void ls_sag_destroy(ls_sag* s);
 
 /* The n torch.randn / randn_like draws of a fused chunk in one launch: tensor i (dense, fp32,
  * numels[i] elements, written in memory order) receives exactly the values torch's CUDA

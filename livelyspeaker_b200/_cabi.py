@@ -19,7 +19,8 @@ IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
-           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
+           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_sag_create", "ls_sag_decode_tc",
+           "ls_sag_launch_count", "ls_sag_destroy", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
            "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align"]
 
 

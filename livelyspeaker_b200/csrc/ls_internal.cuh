@@ -125,6 +125,7 @@ void lsw_destroy(ls_handle* h);
 int lsw_available(const ls_handle* h);
 int lsw_conv(ls_handle* h, int layer, const float* in, const float* bias, float* out, int nb, int Li, int Lo,
              cudaStream_t s);
+int lsw_audio_proj(ls_handle* h, const float* af_cm, int nb, float* A, cudaStream_t s);   // A [nb*34][512] from af [nb][256][34]
 // ls_fused.cu
 int lsf_init(ls_handle* h, cudaStream_t s);            // build bf16 weight tapes; 0 if available
 void lsf_destroy(ls_handle* h);

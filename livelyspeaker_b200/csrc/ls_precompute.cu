@@ -192,7 +192,7 @@ int lsk_cm_to_fm(ls_handle* h, const float* in_cm, float* out_fm, int B, cudaStr
 __global__ void __launch_bounds__(512) cond_proj_kernel(LsWeights w, int JD, int n_spk, int n_emo,
                                                         const float* __restrict__ af_cm, float* __restrict__ origin_x,
                                                         const int64_t* __restrict__ vid, const int64_t* __restrict__ emo,
-                                                        int64_t emo_stride, int mutate_origin, int b0,
+                                                        int64_t emo_stride, int mutate_origin, int b0, int with_A,
                                                         float* __restrict__ A, float* __restrict__ P,
                                                         float* __restrict__ z_mu, float* __restrict__ z_lv,
                                                         float* __restrict__ emo_tok) {
@@ -202,7 +202,8 @@ __global__ void __launch_bounds__(512) cond_proj_kernel(LsWeights w, int JD, int
   float* z_s = ox_s + JD * LS_NPRE;       // [256]
   const int b = b0 + blockIdx.x, c = threadIdx.x;
   const float* afb = af_cm + (size_t)blockIdx.x * LS_AF * LS_F;
-  for (int i = c; i < LS_AF * LS_F; i += 512) af_s[i] = afb[i];
+  if (with_A)
+    for (int i = c; i < LS_AF * LS_F; i += 512) af_s[i] = afb[i];
   float* oxb = origin_x + (size_t)b * JD * LS_F;
   for (int i = c; i < JD * LS_NPRE; i += 512) ox_s[i] = oxb[(i >> 2) * LS_F + (i & 3)];
   long long v = vid[b];
@@ -213,17 +214,19 @@ __global__ void __launch_bounds__(512) cond_proj_kernel(LsWeights w, int JD, int
     for (int i = c; i < JD * LS_F; i += 512)
       if (i % LS_F >= LS_NPRE) oxb[i] = 0.f;
 
-  float acc[LS_F];
+  if (with_A) {          // exact-order fp32 path; the tensor-core path computes A with lsw_audio_proj
+    float acc[LS_F];
 #pragma unroll
-  for (int f = 0; f < LS_F; ++f) acc[f] = 0.f;
-  for (int k = 0; k < LS_AF; ++k) {
-    const float wv = w.w_a_t[(size_t)k * LS_D + c];
+    for (int f = 0; f < LS_F; ++f) acc[f] = 0.f;
+    for (int k = 0; k < LS_AF; ++k) {
+      const float wv = w.w_a_t[(size_t)k * LS_D + c];
 #pragma unroll
-    for (int f = 0; f < LS_F; ++f) acc[f] = fmaf(af_s[k * LS_F + f], wv, acc[f]);
+      for (int f = 0; f < LS_F; ++f) acc[f] = fmaf(af_s[k * LS_F + f], wv, acc[f]);
+    }
+    float* Ab = A + (size_t)b * LS_F * LS_D;
+#pragma unroll
+    for (int f = 0; f < LS_F; ++f) Ab[f * LS_D + c] = acc[f];
   }
-  float* Ab = A + (size_t)b * LS_F * LS_D;
-#pragma unroll
-  for (int f = 0; f < LS_F; ++f) Ab[f * LS_D + c] = acc[f];
 
   float pre[LS_NPRE] = {0.f, 0.f, 0.f, 0.f};
   for (int j = 0; j < JD; ++j) {
@@ -256,8 +259,13 @@ int lsk_cond_proj(ls_handle* h, int B, int b0, const float* af_cm, float* origin
   const size_t smem = (size_t)(LS_AF * LS_F + h->JD * LS_NPRE + LS_SPK) * sizeof(float);
   // the attribute is per DEVICE: set on every launch (one process may drive several GPUs)
   LS_CUDA(h, cudaFuncSetAttribute(cond_proj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const bool tc = lsw_available(h) && ls_get_impl(h) != LS_IMPL_SIMT;
+  if (tc) {
+    const int rc = lsw_audio_proj(h, af_cm, B, h->A + (size_t)b0 * LS_F * LS_D, s);
+    if (rc) return rc;
+  }
   cond_proj_kernel<<<B, 512, smem, s>>>(h->w, h->JD, h->cfg.n_speakers, h->cfg.n_emotions, af_cm, origin_x, vid, emo,
-                                        emo_stride, mutate_origin, b0, h->A, h->P, h->z_mu, h->z_lv, h->emo_tok);
+                                        emo_stride, mutate_origin, b0, tc ? 0 : 1, h->A, h->P, h->z_mu, h->z_lv, h->emo_tok);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
 }

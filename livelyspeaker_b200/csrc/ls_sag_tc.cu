@@ -1,0 +1,253 @@
+// SAG decoder on the tensor cores (round-1 VERDICT "weak" 6): Decoder_TRANSFORMER.forward of
+// scripts/model/motionclip_module.py:137-183 as a handful of launches per layer over ALL clips of the batch:
+//
+//   queries            X = mapping([pre-pose, 1]) + pe                                 (sag_queries_kernel)
+//   cross-attention    ca[l][b] = out_proj(v_proj(z_b))  - the memory is one token, softmax over one key = 1,
+//                      so every layer's cross-attention output is one vector per clip  (sag_cross_kernel, all layers)
+//   per layer          QKV = X W_in^T + b                         rows_gemm  (tcgen05, bf16x3)
+//                      O   = softmax(Q K^T / sqrt(128)) V          sag_attn_kernel (fp32, 34 x 34 per head)
+//                      X   = LN2(LN1(X + O W_o^T + b) + ca[l][b])  rows_gemm + row epilogue
+//                      H   = gelu(X W_1^T + b)                     rows_gemm
+//                      X   = LN3(X + H W_2^T + b)                  rows_gemm + row epilogue
+//   output             out[b, :, t] = mask * (X finallayer^T + b)                      (sag_final_kernel)
+//
+// 111 GFLOP at B = 256 that the one-CTA-per-clip fp32 kernel (ls_sag.cu, kept as the exact-order cross-check) spends
+// 5.2 ms on.  State (weight tapes, workspaces for max_batch clips) lives in an ls_sag handle.
+#include <cstddef>
+#include <string>
+
+#include "ls_internal.cuh"
+#include "ls_rows_gemm.cuh"
+
+namespace {
+
+constexpr int D = 512, T = 34, HD = 128, NH = 4, FF = 1024;
+
+// X[b*34 + t][c] = map_b[c] + pe[t][c] + (t < n_pre ? map_w[c, :] . [x[b, :, t], 1] : 0)
+__global__ void __launch_bounds__(512) sag_queries_kernel(ls_sag_weights w, const float* __restrict__ x, float* __restrict__ X) {
+  const int b = blockIdx.x, c = threadIdx.x;
+  const int JD = w.njoints * w.nfeats;
+  const float* xb = x + (size_t)b * JD * T;
+  const float bm = w.map_b[c];
+  for (int t = 0; t < T; ++t) {
+    float v = bm + w.pe[(size_t)t * w.pe_stride + c];
+    if (t < w.n_pre_poses) {
+      float a = w.map_wt[(size_t)JD * D + c];                    // the indicator bit
+      for (int j = 0; j < JD; ++j) a = fmaf(xb[j * T + t], w.map_wt[(size_t)j * D + c], a);
+      v += a;
+    }
+    X[((size_t)b * T + t) * D + c] = v;
+  }
+}
+
+// ca[l][b][:] = W_o (W_v z_b + b_v) + b_o; block = 8 clips of one layer, thread = output column
+constexpr int CA_CLIPS = 8;
+__global__ void __launch_bounds__(512) sag_cross_kernel(ls_sag_weights w, const float* __restrict__ z, int B, float* __restrict__ ca) {
+  __shared__ float zs[CA_CLIPS][D];
+  __shared__ float vs[CA_CLIPS][D];
+  const ls_sag_layer& L = w.layer[blockIdx.y];
+  const int b0 = blockIdx.x * CA_CLIPS, c = threadIdx.x;
+  for (int i = 0; i < CA_CLIPS; ++i) zs[i][c] = (b0 + i < B) ? z[(size_t)(b0 + i) * D + c] : 0.f;
+  __syncthreads();
+  float a[CA_CLIPS];
+#pragma unroll
+  for (int i = 0; i < CA_CLIPS; ++i) a[i] = 0.f;
+  for (int k = 0; k < D; ++k) {
+    const float wv = L.ca_v_wt[(size_t)k * D + c];
+#pragma unroll
+    for (int i = 0; i < CA_CLIPS; ++i) a[i] = fmaf(zs[i][k], wv, a[i]);
+  }
+  const float bv = L.ca_v_b[c];
+#pragma unroll
+  for (int i = 0; i < CA_CLIPS; ++i) vs[i][c] = a[i] + bv;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < CA_CLIPS; ++i) a[i] = 0.f;
+  for (int k = 0; k < D; ++k) {
+    const float wv = L.ca_out_wt[(size_t)k * D + c];
+#pragma unroll
+    for (int i = 0; i < CA_CLIPS; ++i) a[i] = fmaf(vs[i][k], wv, a[i]);
+  }
+  const float bo = L.ca_out_b[c];
+  for (int i = 0; i < CA_CLIPS; ++i)
+    if (b0 + i < B) ca[((size_t)blockIdx.y * B + b0 + i) * D + c] = a[i] + bo;
+}
+
+// one (clip, head): O[t][e] = sum_s softmax_s(q_t . k_s / sqrt(128)) v[s][e]; thread = e
+__global__ void __launch_bounds__(HD) sag_attn_kernel(const float* __restrict__ qkv, float* __restrict__ O) {
+  __shared__ float q[T][HD];
+  __shared__ float k[T][HD + 1];
+  __shared__ float p[T][T + 2];
+  float v[T];                                   // this thread's column of V stays in registers
+  const int b = blockIdx.x, h = blockIdx.y, e = threadIdx.x;
+  const float* src = qkv + (size_t)b * T * 3 * D + h * HD + e;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    q[t][e] = src[(size_t)t * 3 * D] * 0.08838834764831845f;     // 1 / sqrt(128)
+    k[t][e] = src[(size_t)t * 3 * D + D];
+    v[t] = src[(size_t)t * 3 * D + 2 * D];
+  }
+  __syncthreads();
+  for (int i = e; i < T * T; i += HD) {
+    const int t = i / T, s = i - t * T;
+    float a = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < HD; ++j) a = fmaf(q[t][j], k[s][j], a);
+    p[t][s] = a;
+  }
+  __syncthreads();
+  if (e < T) {
+    float m = -INFINITY;
+    for (int s = 0; s < T; ++s) m = fmaxf(m, p[e][s]);
+    float sum = 0.f;
+    for (int s = 0; s < T; ++s) {
+      const float ex = expf(p[e][s] - m);
+      p[e][s] = ex;
+      sum += ex;
+    }
+    const float inv = 1.f / sum;
+    for (int s = 0; s < T; ++s) p[e][s] *= inv;
+  }
+  __syncthreads();
+  float* dst = O + (size_t)b * T * D + h * HD + e;
+  for (int t = 0; t < T; ++t) {
+    float o = 0.f;
+#pragma unroll
+    for (int s = 0; s < T; ++s) o = fmaf(p[t][s], v[s], o);
+    dst[(size_t)t * D] = o;
+  }
+}
+
+// out[b][j][t] = mask[b][t] ? fin_b[j] + X[b*34 + t] . fin_w[j] : 0
+__global__ void __launch_bounds__(256) sag_final_kernel(ls_sag_weights w, const float* __restrict__ X,
+                                                        const uint8_t* __restrict__ mask, float* __restrict__ out) {
+  extern __shared__ float xs[];                  // [34][513]
+  const int b = blockIdx.x, JD = w.njoints * w.nfeats;
+  for (int i = threadIdx.x; i < T * D; i += 256) xs[(i >> 9) * (D + 1) + (i & 511)] = X[(size_t)b * T * D + i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < JD * T; i += 256) {
+    const int j = i / T, t = i - j * T;
+    float a = w.fin_b[j];
+    const float* xr = xs + t * (D + 1);
+    for (int k = 0; k < D; ++k) a = fmaf(xr[k], w.fin_wt[(size_t)k * JD + j], a);
+    if (mask != nullptr && !mask[(size_t)b * T + t]) a = 0.f;
+    out[(size_t)b * JD * T + i] = a;
+  }
+}
+
+}  // namespace
+
+struct ls_sag {
+  ls_sag_weights w{};
+  int device = 0, max_batch = 0;
+  uint8_t* tape = nullptr;                       // all layers: [in_proj | out_proj | linear1 | linear2]
+  size_t layer_bytes = 0, off_out = 0, off_l1 = 0, off_l2 = 0;
+  float *X = nullptr, *QKV = nullptr, *O = nullptr, *H = nullptr, *CA = nullptr;
+  int64_t launches = 0;
+};
+
+extern "C" void ls_sag_destroy(ls_sag* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (void* p : {(void*)s->tape, (void*)s->X, (void*)s->QKV, (void*)s->O, (void*)s->H, (void*)s->CA})
+    if (p) cudaFree(p);
+  delete s;
+}
+
+#define SAG_CUDA(expr)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess) {                                                                                \
+      rc = ls_fail(nullptr, LS_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));   \
+      goto fail;                                                                                             \
+    }                                                                                                        \
+  } while (0)
+
+extern "C" int ls_sag_create(ls_sag** out, const ls_sag_weights* w, int32_t max_batch, int32_t device, void* stream) {
+  if (!out || !w || max_batch < 1) return ls_fail(nullptr, LS_EINVAL, "ls_sag_create: bad argument");
+  *out = nullptr;
+  if (w->n_frames != T || w->latent_dim != D || w->ff_size != FF || w->n_heads != NH || w->n_layers < 1 ||
+      w->n_layers > LS_SAG_MAX_LAYERS || w->n_pre_poses < 0 || w->n_pre_poses > T)
+    return ls_fail(nullptr, LS_EUNSUPPORTED, "ls_sag_create: built for 34 frames, d=512, ff=1024, 4 heads, <= %d layers",
+                   LS_SAG_MAX_LAYERS);
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10)
+    return ls_fail(nullptr, LS_EUNSUPPORTED, "ls_sag_create: device %d is not sm_100", device);
+  if (cudaSetDevice(device) != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "cudaSetDevice failed");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = LS_OK;
+  ls_sag* s = new ls_sag();
+  s->w = *w;
+  s->device = device;
+  s->max_batch = max_batch;
+  const size_t b_in = lsrg::rows_tape_bytes(3 * D, D), b_out = lsrg::rows_tape_bytes(D, D), b_l1 = lsrg::rows_tape_bytes(FF, D),
+               b_l2 = lsrg::rows_tape_bytes(D, FF);
+  s->off_out = b_in;
+  s->off_l1 = b_in + b_out;
+  s->off_l2 = b_in + b_out + b_l1;
+  s->layer_bytes = b_in + b_out + b_l1 + b_l2;
+  const size_t rows = (size_t)max_batch * T;
+  SAG_CUDA(cudaMalloc(&s->tape, s->layer_bytes * w->n_layers));
+  SAG_CUDA(cudaMalloc(&s->X, rows * D * sizeof(float)));
+  SAG_CUDA(cudaMalloc(&s->QKV, rows * 3 * D * sizeof(float)));
+  SAG_CUDA(cudaMalloc(&s->O, rows * D * sizeof(float)));
+  SAG_CUDA(cudaMalloc(&s->H, rows * FF * sizeof(float)));
+  SAG_CUDA(cudaMalloc(&s->CA, (size_t)w->n_layers * max_batch * D * sizeof(float)));
+  for (int l = 0; l < w->n_layers; ++l) {
+    const ls_sag_layer& L = w->layer[l];
+    uint8_t* base = s->tape + s->layer_bytes * l;
+    lsrg::build_rows_tape_kernel<<<256, 256, 0, st>>>(L.sa_in_wt, 3 * D, D, base);
+    lsrg::build_rows_tape_kernel<<<256, 256, 0, st>>>(L.sa_out_wt, D, D, base + s->off_out);
+    lsrg::build_rows_tape_kernel<<<256, 256, 0, st>>>(L.l1_wt, FF, D, base + s->off_l1);
+    lsrg::build_rows_tape_kernel<<<256, 256, 0, st>>>(L.l2_wt, D, FF, base + s->off_l2);
+  }
+  SAG_CUDA(cudaGetLastError());
+  SAG_CUDA(cudaFuncSetAttribute(lsrg::rows_gemm_kernel<lsrg::ARowMajor, lsrg::EpiStore<false>>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsrg::SMEM));
+  SAG_CUDA(cudaFuncSetAttribute(lsrg::rows_gemm_kernel<lsrg::ARowMajor, lsrg::EpiStore<true>>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsrg::SMEM));
+  SAG_CUDA(cudaFuncSetAttribute(lsrg::rows_gemm_kernel<lsrg::ARowMajor, lsrg::EpiResLN<false>>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsrg::SMEM));
+  SAG_CUDA(cudaFuncSetAttribute(lsrg::rows_gemm_kernel<lsrg::ARowMajor, lsrg::EpiResLN<true>>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsrg::SMEM));
+  SAG_CUDA(cudaFuncSetAttribute(sag_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T * (D + 1) * (int)sizeof(float)));
+  *out = s;
+  return LS_OK;
+fail:
+  ls_sag_destroy(s);
+  return rc;
+}
+
+extern "C" int64_t ls_sag_launch_count(const ls_sag* s) { return s ? s->launches : 0; }
+
+extern "C" int ls_sag_decode_tc(ls_sag* s, int32_t B, const float* x, const float* z, const uint8_t* mask, float* out,
+                                void* stream) {
+  if (!s || !x || !z || !out || B < 1) return ls_fail(nullptr, LS_EINVAL, "ls_sag_decode_tc: bad argument");
+  if (B > s->max_batch) return ls_fail(nullptr, LS_EINVAL, "ls_sag_decode_tc: batch %d exceeds max_batch %d", B, s->max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const ls_sag_weights& w = s->w;
+  const int rows = B * T, RT = (rows + 127) / 128;
+  using namespace lsrg;
+  sag_queries_kernel<<<B, 512, 0, st>>>(w, x, s->X);
+  sag_cross_kernel<<<dim3((B + CA_CLIPS - 1) / CA_CLIPS, w.n_layers), 512, 0, st>>>(w, z, B, s->CA);
+  s->launches += 2;
+  for (int l = 0; l < w.n_layers; ++l) {
+    const ls_sag_layer& L = w.layer[l];
+    const uint8_t* base = s->tape + s->layer_bytes * l;
+    rows_gemm_kernel<<<dim3(RT, 3), NTHREADS, SMEM, st>>>(ARowMajor{s->X, D}, base, rows, D, EpiStore<false>{s->QKV, 3 * D, L.sa_in_b});
+    sag_attn_kernel<<<dim3(B, NH), HD, 0, st>>>(s->QKV, s->O);
+    rows_gemm_kernel<<<dim3(RT, 1), NTHREADS, SMEM, st>>>(
+        ARowMajor{s->O, D}, base + s->off_out, rows, D,
+        EpiResLN<true>{s->X, s->X, L.sa_out_b, L.n1_w, L.n1_b, s->CA + (size_t)l * B * D, T, L.n2_w, L.n2_b});
+    rows_gemm_kernel<<<dim3(RT, 2), NTHREADS, SMEM, st>>>(ARowMajor{s->X, D}, base + s->off_l1, rows, D, EpiStore<true>{s->H, FF, L.l1_b});
+    rows_gemm_kernel<<<dim3(RT, 1), NTHREADS, SMEM, st>>>(
+        ARowMajor{s->H, FF}, base + s->off_l2, rows, FF,
+        EpiResLN<false>{s->X, s->X, L.l2_b, L.n3_w, L.n3_b, nullptr, T, nullptr, nullptr});
+    s->launches += 5;
+  }
+  sag_final_kernel<<<B, 256, T * (D + 1) * sizeof(float), st>>>(w, s->X, mask, out);
+  s->launches += 1;
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_sag_decode_tc: %s", cudaGetErrorString(e));
+  return LS_OK;
+}

@@ -13,6 +13,7 @@
 #include <cuda_bf16.h>
 
 #include "ls_internal.cuh"
+#include "ls_rows_gemm.cuh"
 #include "ls_tc.cuh"
 
 using namespace lstc;
@@ -151,6 +152,7 @@ __global__ void build_conv_tape_kernel(const float* __restrict__ w, int Co, int 
 
 struct WavTc {
   uint8_t* tape[3] = {nullptr, nullptr, nullptr};
+  uint8_t* tape_a = nullptr;      // audio half of input_mapping (W_a [512 x 256]) for lsw_audio_proj
   bool attr_done = false;
 };
 
@@ -171,6 +173,7 @@ void lsw_destroy(ls_handle* h) {
     WavTc* w = static_cast<WavTc*>(h->wavtc);
     for (auto& t : w->tape)
       if (t) cudaFree(t);
+    if (w->tape_a) cudaFree(w->tape_a);
     delete w;
     h->wavtc = nullptr;
   }
@@ -189,14 +192,23 @@ int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s) {
         delete wt;
         return ls_fail(h, LS_ENOMEM, "WavEncoder weight tape");
       }
+    if (cudaMalloc(&wt->tape_a, lsrg::rows_tape_bytes(LS_D, LS_AF)) != cudaSuccess) {
+      for (auto& t : wt->tape) cudaFree(t);
+      delete wt;
+      return ls_fail(h, LS_ENOMEM, "audio projection weight tape");
+    }
     h->wavtc = wt;
   }
   if (!wt->attr_done) {
     LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<64>::SMEM));
     LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<128>::SMEM));
     LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay<256>::SMEM));
+    LS_CUDA(h, cudaFuncSetAttribute(lsrg::rows_gemm_kernel<lsrg::AChanMajor34, lsrg::EpiStore<false>>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsrg::SMEM));
     wt->attr_done = true;
   }
+  lsrg::build_rows_tape_kernel<<<64, 256, 0, s>>>(h->w.w_a_t, LS_D, LS_AF, wt->tape_a);
+  LS_LAUNCH_CHECK(h);
   for (int i = 0; i < 3; ++i) {
     build_conv_tape_kernel<<<64, 256, 0, s>>>(w[i], CO[i], CI[i], wt->tape[i]);
     LS_LAUNCH_CHECK(h);
@@ -214,4 +226,16 @@ int lsw_conv(ls_handle* h, int layer, const float* in, const float* bias, float*
     case 2: return launch_conv<256>(h, in, wt->tape[2], bias, out, nb, 128, Li, Lo, s);
   }
   return ls_fail(h, LS_EINVAL, "layer %d", layer);
+}
+
+// A[b, f, :] = af[b, :, f] . W_a^T (RAG.py:184-192, the audio columns of input_mapping; cond pass only): one GEMM over
+// the nb * 34 frame rows of a WavEncoder chunk, A operand read in the encoder's own channel-major layout.
+int lsw_audio_proj(ls_handle* h, const float* af_cm, int nb, float* A, cudaStream_t s) {
+  WavTc* wt = static_cast<WavTc*>(h->wavtc);
+  if (!wt) return ls_fail(h, LS_EUNSUPPORTED, "tensor-core precompute not initialised");
+  const int rows = nb * LS_F;
+  lsrg::rows_gemm_kernel<<<dim3((rows + 127) / 128, 1), lsrg::NTHREADS, lsrg::SMEM, s>>>(
+      lsrg::AChanMajor34{af_cm, LS_AF}, wt->tape_a, rows, LS_AF, lsrg::EpiStore<false>{A, LS_D, nullptr});
+  LS_LAUNCH_CHECK(h);
+  return LS_OK;
 }

@@ -4,8 +4,10 @@ Mirror of the reference's ``Decoder_TRANSFORMER`` (scripts/model/motionclip_modu
 same ``state_dict`` keys and shapes (the torch ``nn.TransformerDecoder`` modules are kept as parameter
 containers only), same ``forward(batch, use_text_emb=False)`` contract - ``batch['z']`` (CLIP text feature),
 ``batch['x']`` (pose clip whose first ``n_pre_poses`` frames condition the decoder), ``batch['mask']`` ->
-``batch['output']`` / ``batch['txt_output']`` [B, J, D, F] and ``batch['final_z']``.  The math runs in
-``ls_sag_decode`` (csrc/ls_sag.cu) through the C ABI; there is no PyTorch implementation of it here.
+``batch['output']`` / ``batch['txt_output']`` [B, J, D, F] and ``batch['final_z']``.  The math runs through the C
+ABI: ``ls_sag_decode_tc`` (csrc/ls_sag_tc.cu: tcgen05 GEMMs, bf16x3, one ``ls_sag`` handle per weight set) by default,
+``ls_sag_decode`` (csrc/ls_sag.cu: exact-order fp32, one CTA per clip) with ``decoder.impl = 'simt'``; there is no
+PyTorch implementation of it here.
 """
 import ctypes
 from ctypes import POINTER, c_int32, c_int64, c_void_p
@@ -60,7 +62,43 @@ class Decoder_TRANSFORMER(nn.Module):
         self.finallayer = nn.Linear(latent_dim, self.input_feats)
         self.mapping = nn.Linear(self.input_feats + 1, latent_dim)
         self.n_pre_poses = n_pre_poses
+        self.impl = "tc"              # 'tc': tensor cores (ls_sag_decode_tc); 'simt': exact-order fp32 (ls_sag_decode)
         self._packed = None
+        self._tc = None               # (pack key, max_batch, ls_sag*)
+
+    def __del__(self):
+        self._drop_tc()
+
+    def _drop_tc(self):
+        tc, self._tc = getattr(self, "_tc", None), None
+        if tc is not None:
+            try:
+                _cabi.load_library().ls_sag_destroy(tc[2])
+            except Exception:      # interpreter shutdown
+                pass
+
+    def _tc_handle(self, lib, W, key, bs, dev):
+        """The ls_sag handle of the current weights, rebuilt when they changed or the batch outgrew its workspaces."""
+        if self._tc is not None and self._tc[0] == key and self._tc[1] >= bs:
+            return self._tc[2]
+        self._drop_tc()
+        lib.ls_sag_create.argtypes = [POINTER(c_void_p), POINTER(LsSagWeights), c_int32, c_int32, c_void_p]
+        lib.ls_sag_decode_tc.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        lib.ls_sag_destroy.argtypes = [c_void_p]
+        lib.ls_sag_destroy.restype = None
+        lib.ls_sag_launch_count.argtypes = [c_void_p]
+        lib.ls_sag_launch_count.restype = c_int64
+        h = c_void_p()
+        rc = lib.ls_sag_create(ctypes.byref(h), ctypes.byref(W), int(bs), dev.index or 0,
+                               c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc != 0:
+            raise _cabi.LsError("libls_b200 error %d: %s" % (rc, lib.ls_last_error(None).decode()))
+        self._tc = (key, int(bs), h)
+        return h
+
+    def launch_count(self):
+        """Kernels launched by the tensor-core handle since it was built (0 before the first decode)."""
+        return int(_cabi.load_library().ls_sag_launch_count(self._tc[2])) if self._tc is not None else 0
 
     # ------------------------------------------------------------------ weights -> ls_sag_weights
     def _pack(self, device):
@@ -127,9 +165,14 @@ class Decoder_TRANSFORMER(nn.Module):
         m8 = mask.to(dev).to(torch.uint8).contiguous()
         out = torch.empty(bs, self.njoints, self.nfeats, nframes, dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            rc = lib.ls_sag_decode(ctypes.byref(W), bs, c_void_p(x.data_ptr()), c_void_p(zf.data_ptr()),
-                                   c_void_p(m8.data_ptr()), c_void_p(out.data_ptr()),
-                                   c_void_p(torch.cuda.current_stream().cuda_stream))
+            args = (bs, c_void_p(x.data_ptr()), c_void_p(zf.data_ptr()), c_void_p(m8.data_ptr()),
+                    c_void_p(out.data_ptr()), c_void_p(torch.cuda.current_stream().cuda_stream))
+            if self.impl == "simt":
+                rc = lib.ls_sag_decode(ctypes.byref(W), *args)
+            elif self.impl == "tc":
+                rc = lib.ls_sag_decode_tc(self._tc_handle(lib, W, self._packed[0], bs, dev), *args)
+            else:
+                raise ValueError("impl must be 'tc' or 'simt'")
         if rc != 0:
             raise _cabi.LsError("libls_b200 error %d: %s" % (rc, lib.ls_last_error(None).decode()))
         # the reference returns output.permute(1, 2, 3, 0) of a [F,B,J,D] tensor (motionclip_module.py:181): same

@@ -197,14 +197,17 @@ def test_plms_loops_ted(tag, golden_plms):
         diffusion.plms_sample(cfg, got, torch.zeros(2, dtype=torch.long, device=DEV), cond_fn_with_grad=True)
 
 
-def test_sag_decoder(golden_sag):
-    """Decoder_TRANSFORMER.forward through ls_sag_decode against the reference module's fixture and the oracle;
-    then config-3 style use: its output as init_image of a RAG loop, B=256 batch independence."""
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_sag_decoder(golden_sag, impl):
+    """Decoder_TRANSFORMER.forward through ls_sag_decode_tc (tensor cores, the default) / ls_sag_decode (exact-order
+    fp32) against the reference module's fixture and the oracle; then config-3 style use: its output as init_image of
+    a RAG loop, B=256 batch independence (bit-exact on both paths: a clip's result does not depend on its row tile)."""
     from oracle import sag_oracle
     sd = synthetic.synth_sag_state_dict(seed=3)
     dec = ls.Decoder_TRANSFORMER(latent_dim=512, n_pre_poses=4, use_style=False)
     dec.load_state_dict(sd, strict=True)
     dec = dec.to(DEV).eval()
+    dec.impl = impl
     x, z, mask = (torch.from_numpy(golden_sag[k]) for k in ("x", "z", "mask"))
     batch = dec({"x": x.to(DEV), "z": z.to(DEV), "mask": mask.to(DEV)})
     assert set(batch) >= {"output", "final_z"} and batch["output"].shape == (3, 9, 3, 34)
@@ -223,6 +226,11 @@ def test_sag_decoder(golden_sag):
     assert torch.equal(big[idx], small)
     with torch.no_grad():
         _close(small, sag_oracle.decode(sd, xb[idx], zb[idx], mb[idx]))
+    if impl == "tc":        # 2 + 5 per layer + 1 launches per decode, handle rebuilt once (batch 3 -> 256)
+        assert dec.launch_count() == 2 * 18
+        dec.impl = "simt"
+        _close(big, dec({"x": xb.to(DEV), "z": zb.to(DEV), "mask": mb.to(DEV)})["output"])
+        dec.impl = "tc"
     # its output drives the RAG loop as init_image (scripts/test_LivelySpeaker_ted.py:88-113)
     dims, _, cfg, diffusion = build("ted", "ddim100")
     y = synthetic.synth_cond(dims, 2, device=DEV)

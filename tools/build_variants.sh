@@ -11,7 +11,7 @@ FLAGS="$ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr"
 make -j8 libls_b200.so > /dev/null
 build() {  # name, extra flags
   $NVCC $FLAGS $2 -c ls_fused.cu -o /tmp/ls_fused_$1.o
-  $NVCC $ARCH -shared -o libls_$1.so ls_api.o ls_precompute.o ls_denoise_simt.o ls_update.o ls_wavenc_tc.o ls_sag.o ls_randn.o ls_metrics.o /tmp/ls_fused_$1.o
+  $NVCC $ARCH -shared -o libls_$1.so ls_api.o ls_precompute.o ls_denoise_simt.o ls_update.o ls_wavenc_tc.o ls_sag.o ls_sag_tc.o ls_randn.o ls_metrics.o /tmp/ls_fused_$1.o
 }
 build prof "-DLS_MMA_PROF=1" &
 build mc "-DLS_MULTICAST=1 -DLS_MMA_PROF=1" &
