@@ -3,7 +3,8 @@
 //
 //   queries            X = mapping([pre-pose, 1]) + pe                                 (sag_queries_kernel)
 //   cross-attention    ca[l][b] = out_proj(v_proj(z_b))  - the memory is one token, softmax over one key = 1,
-//                      so every layer's cross-attention output is one vector per clip  (sag_cross_kernel, all layers)
+//                      so every layer's cross-attention output is one vector per clip, ONE folded matrix per layer
+//                      (sag_cross_kernel, all layers in one launch)
 //   per layer          QKV = X W_in^T + b                         rows_gemm  (tcgen05, bf16x3)
 //                      O   = softmax(Q K^T / sqrt(128)) V          sag_attn_kernel (fp32, 34 x 34 per head)
 //                      X   = LN2(LN1(X + O W_o^T + b) + ca[l][b])  rows_gemm + row epilogue
@@ -14,6 +15,7 @@
 // 111 GFLOP at B = 256 that the one-CTA-per-clip fp32 kernel (ls_sag.cu, kept as the exact-order cross-check) spends
 // 5.2 ms on.  State (weight tapes, workspaces for max_batch clips) lives in an ls_sag handle.
 #include <cstddef>
+#include <cstdlib>
 #include <string>
 
 #include "ls_internal.cuh"
@@ -29,54 +31,67 @@ __global__ void __launch_bounds__(512) sag_queries_kernel(ls_sag_weights w, cons
   const int JD = w.njoints * w.nfeats;
   const float* xb = x + (size_t)b * JD * T;
   const float bm = w.map_b[c];
-  for (int t = 0; t < T; ++t) {
-    float v = bm + w.pe[(size_t)t * w.pe_stride + c];
-    if (t < w.n_pre_poses) {
-      float a = w.map_wt[(size_t)JD * D + c];                    // the indicator bit
-      for (int j = 0; j < JD; ++j) a = fmaf(xb[j * T + t], w.map_wt[(size_t)j * D + c], a);
-      v += a;
-    }
-    X[((size_t)b * T + t) * D + c] = v;
+  float v[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) v[t] = bm + w.pe[(size_t)t * w.pe_stride + c];     // 34 independent loads in flight
+  for (int t = 0; t < w.n_pre_poses; ++t) {
+    float a = w.map_wt[(size_t)JD * D + c];                    // the indicator bit
+#pragma unroll 8
+    for (int j = 0; j < JD; ++j) a = fmaf(xb[j * T + t], w.map_wt[(size_t)j * D + c], a);
+#pragma unroll
+    for (int u = 0; u < T; ++u)
+      if (u == t) v[u] += a;
   }
+#pragma unroll
+  for (int t = 0; t < T; ++t) X[((size_t)b * T + t) * D + c] = v[t];
 }
 
-// ca[l][b][:] = W_o (W_v z_b + b_v) + b_o; block = 8 clips of one layer, thread = output column
-constexpr int CA_CLIPS = 8;
-__global__ void __launch_bounds__(512) sag_cross_kernel(ls_sag_weights w, const float* __restrict__ z, int B, float* __restrict__ ca) {
-  __shared__ float zs[CA_CLIPS][D];
-  __shared__ float vs[CA_CLIPS][D];
-  const ls_sag_layer& L = w.layer[blockIdx.y];
-  const int b0 = blockIdx.x * CA_CLIPS, c = threadIdx.x;
-  for (int i = 0; i < CA_CLIPS; ++i) zs[i][c] = (b0 + i < B) ? z[(size_t)(b0 + i) * D + c] : 0.f;
+// Cross-attention over ONE memory token: ca[l][b] = W_o (W_v z_b + b_v) + b_o = W_c z_b + b_c with the per-layer
+// products W_c = W_o W_v, b_c = W_o b_v + b_o formed once per weight set (fp64 accumulation, sag_cross_fold_kernel).
+// wct[l][k][n] = W_c[n][k].  block = 16 clips x 128 output columns of one layer, thread = column.
+__global__ void sag_cross_fold_kernel(ls_sag_layer L, float* __restrict__ wct, float* __restrict__ bc) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;        // k == D: the bias row
+  if (n >= D) return;
+  double a = 0.0;
+  for (int m = 0; m < D; ++m)
+    a += (double)(k < D ? L.ca_v_wt[(size_t)k * D + m] : L.ca_v_b[m]) * (double)L.ca_out_wt[(size_t)m * D + n];
+  if (k < D)
+    wct[(size_t)k * D + n] = (float)a;
+  else
+    bc[n] = (float)(a + (double)L.ca_out_b[n]);
+}
+constexpr int CA_CLIPS = 16;
+__global__ void __launch_bounds__(128) sag_cross_kernel(const float* __restrict__ wct, const float* __restrict__ bc,
+                                                        const float* __restrict__ z, int B, float* __restrict__ ca) {
+  __shared__ __align__(16) float zs[CA_CLIPS][D];
+  const int l = blockIdx.z, b0 = blockIdx.x * CA_CLIPS, n = blockIdx.y * 128 + threadIdx.x;
+#pragma unroll
+  for (int i = threadIdx.x; i < CA_CLIPS * D / 4; i += 128) {      // 16 independent float4 loads per thread
+    const int e = 4 * i;
+    *reinterpret_cast<float4*>(&zs[e >> 9][e & 511]) = (b0 + (e >> 9) < B) ? *reinterpret_cast<const float4*>(z + (size_t)b0 * D + e)
+                                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncthreads();
+  const float* wl = wct + (size_t)l * D * D + n;
   float a[CA_CLIPS];
 #pragma unroll
   for (int i = 0; i < CA_CLIPS; ++i) a[i] = 0.f;
+#pragma unroll 8
   for (int k = 0; k < D; ++k) {
-    const float wv = L.ca_v_wt[(size_t)k * D + c];
+    const float wv = wl[(size_t)k * D];
 #pragma unroll
     for (int i = 0; i < CA_CLIPS; ++i) a[i] = fmaf(zs[i][k], wv, a[i]);
   }
-  const float bv = L.ca_v_b[c];
+  const float bo = bc[l * D + n];
 #pragma unroll
-  for (int i = 0; i < CA_CLIPS; ++i) vs[i][c] = a[i] + bv;
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < CA_CLIPS; ++i) a[i] = 0.f;
-  for (int k = 0; k < D; ++k) {
-    const float wv = L.ca_out_wt[(size_t)k * D + c];
-#pragma unroll
-    for (int i = 0; i < CA_CLIPS; ++i) a[i] = fmaf(vs[i][k], wv, a[i]);
-  }
-  const float bo = L.ca_out_b[c];
   for (int i = 0; i < CA_CLIPS; ++i)
-    if (b0 + i < B) ca[((size_t)blockIdx.y * B + b0 + i) * D + c] = a[i] + bo;
+    if (b0 + i < B) ca[((size_t)l * B + b0 + i) * D + n] = a[i] + bo;
 }
 
 // one (clip, head): O[t][e] = sum_s softmax_s(q_t . k_s / sqrt(128)) v[s][e]; thread = e
 __global__ void __launch_bounds__(HD) sag_attn_kernel(const float* __restrict__ qkv, float* __restrict__ O) {
-  __shared__ float q[T][HD];
-  __shared__ float k[T][HD + 1];
+  __shared__ __align__(16) float q[T][HD];
+  __shared__ __align__(16) float k[T][HD + 4];
   __shared__ float p[T][T + 2];
   float v[T];                                   // this thread's column of V stays in registers
   const int b = blockIdx.x, h = blockIdx.y, e = threadIdx.x;
@@ -88,12 +103,32 @@ __global__ void __launch_bounds__(HD) sag_attn_kernel(const float* __restrict__ 
     v[t] = src[(size_t)t * 3 * D + 2 * D];
   }
   __syncthreads();
-  for (int i = e; i < T * T; i += HD) {
-    const int t = i / T, s = i - t * T;
-    float a = 0.f;
-#pragma unroll 8
-    for (int j = 0; j < HD; ++j) a = fmaf(q[t][j], k[s][j], a);
-    p[t][s] = a;
+  if (e < 17 * 6) {                              // scores: thread = 2 query rows x 6 keys (s = sg, sg + 6, ...)
+    const int t0 = 2 * (e / 6), sg = e % 6;
+    float a[2][6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) a[0][i] = a[1][i] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < HD; j += 4) {
+      const float4 qa = *reinterpret_cast<const float4*>(&q[t0][j]), qb = *reinterpret_cast<const float4*>(&q[t0 + 1][j]);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int s = sg + 6 * i;
+        if (s < T) {
+          const float4 kv = *reinterpret_cast<const float4*>(&k[s][j]);
+          a[0][i] = fmaf(qa.x, kv.x, fmaf(qa.y, kv.y, fmaf(qa.z, kv.z, fmaf(qa.w, kv.w, a[0][i]))));
+          a[1][i] = fmaf(qb.x, kv.x, fmaf(qb.y, kv.y, fmaf(qb.z, kv.z, fmaf(qb.w, kv.w, a[1][i]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int s = sg + 6 * i;
+      if (s < T) {
+        p[t0][s] = a[0][i];
+        p[t0 + 1][s] = a[1][i];
+      }
+    }
   }
   __syncthreads();
   if (e < T) {
@@ -118,20 +153,51 @@ __global__ void __launch_bounds__(HD) sag_attn_kernel(const float* __restrict__ 
   }
 }
 
-// out[b][j][t] = mask[b][t] ? fin_b[j] + X[b*34 + t] . fin_w[j] : 0
+// out[b][j][t] = mask[b][t] ? fin_b[j] + X[b*34 + t] . fin_w[j] : 0; one clip per block, 32 outputs j at a time with
+// their weights staged in shared memory (rows padded to 513 floats: conflict-free for both operands)
+constexpr int FIN_J = 32;
+constexpr int FIN_SMEM = (T + FIN_J) * (D + 1) * (int)sizeof(float);
 __global__ void __launch_bounds__(256) sag_final_kernel(ls_sag_weights w, const float* __restrict__ X,
                                                         const uint8_t* __restrict__ mask, float* __restrict__ out) {
-  extern __shared__ float xs[];                  // [34][513]
+  extern __shared__ float xs[];                  // [34][513] tokens, then [32][513] weights
+  float* ws = xs + T * (D + 1);
   const int b = blockIdx.x, JD = w.njoints * w.nfeats;
-  for (int i = threadIdx.x; i < T * D; i += 256) xs[(i >> 9) * (D + 1) + (i & 511)] = X[(size_t)b * T * D + i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < JD * T; i += 256) {
-    const int j = i / T, t = i - j * T;
-    float a = w.fin_b[j];
-    const float* xr = xs + t * (D + 1);
-    for (int k = 0; k < D; ++k) a = fmaf(xr[k], w.fin_wt[(size_t)k * JD + j], a);
-    if (mask != nullptr && !mask[(size_t)b * T + t]) a = 0.f;
-    out[(size_t)b * JD * T + i] = a;
+  {
+    const float4* src = reinterpret_cast<const float4*>(X + (size_t)b * T * D);
+    float4 v[17];                              // 34 * 512 / 4 / 256 = 17 independent loads in flight
+#pragma unroll
+    for (int i = 0; i < 17; ++i) v[i] = src[threadIdx.x + 256 * i];
+#pragma unroll
+    for (int i = 0; i < 17; ++i) {
+      const int e = 4 * (threadIdx.x + 256 * i);
+      float* d = xs + (e >> 9) * (D + 1) + (e & 511);
+      d[0] = v[i].x; d[1] = v[i].y; d[2] = v[i].z; d[3] = v[i].w;
+    }
+  }
+  for (int j0 = 0; j0 < JD; j0 += FIN_J) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < FIN_J * D; i += 256) {       // fin_wt is [k][JD]: 32 consecutive j per k
+      const int k = i >> 5, jj = i & 31;
+      ws[jj * (D + 1) + k] = (j0 + jj < JD) ? w.fin_wt[(size_t)k * JD + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FIN_J * T; i += 256) {
+      const int jj = i / T, t = i - jj * T, j = j0 + jj;
+      if (j >= JD) continue;
+      const float* xr = xs + t * (D + 1);
+      const float* wr = ws + jj * (D + 1);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+      for (int k = 0; k < D; k += 4) {
+        a0 = fmaf(xr[k], wr[k], a0);
+        a1 = fmaf(xr[k + 1], wr[k + 1], a1);
+        a2 = fmaf(xr[k + 2], wr[k + 2], a2);
+        a3 = fmaf(xr[k + 3], wr[k + 3], a3);
+      }
+      float a = w.fin_b[j] + ((a0 + a1) + (a2 + a3));
+      if (mask != nullptr && !mask[(size_t)b * T + t]) a = 0.f;
+      out[((size_t)b * JD + j) * T + t] = a;
+    }
   }
 }
 
@@ -143,13 +209,14 @@ struct ls_sag {
   uint8_t* tape = nullptr;                       // all layers: [in_proj | out_proj | linear1 | linear2]
   size_t layer_bytes = 0, off_out = 0, off_l1 = 0, off_l2 = 0;
   float *X = nullptr, *QKV = nullptr, *O = nullptr, *H = nullptr, *CA = nullptr;
+  float *wct = nullptr, *bc = nullptr;           // folded cross-attention: [L][512][512], [L][512]
   int64_t launches = 0;
 };
 
 extern "C" void ls_sag_destroy(ls_sag* s) {
   if (!s) return;
   cudaSetDevice(s->device);
-  for (void* p : {(void*)s->tape, (void*)s->X, (void*)s->QKV, (void*)s->O, (void*)s->H, (void*)s->CA})
+  for (void* p : {(void*)s->tape, (void*)s->X, (void*)s->QKV, (void*)s->O, (void*)s->H, (void*)s->CA, (void*)s->wct, (void*)s->bc})
     if (p) cudaFree(p);
   delete s;
 }
@@ -193,6 +260,8 @@ extern "C" int ls_sag_create(ls_sag** out, const ls_sag_weights* w, int32_t max_
   SAG_CUDA(cudaMalloc(&s->O, rows * D * sizeof(float)));
   SAG_CUDA(cudaMalloc(&s->H, rows * FF * sizeof(float)));
   SAG_CUDA(cudaMalloc(&s->CA, (size_t)w->n_layers * max_batch * D * sizeof(float)));
+  SAG_CUDA(cudaMalloc(&s->wct, (size_t)w->n_layers * D * D * sizeof(float)));
+  SAG_CUDA(cudaMalloc(&s->bc, (size_t)w->n_layers * D * sizeof(float)));
   for (int l = 0; l < w->n_layers; ++l) {
     const ls_sag_layer& L = w->layer[l];
     uint8_t* base = s->tape + s->layer_bytes * l;
@@ -200,6 +269,7 @@ extern "C" int ls_sag_create(ls_sag** out, const ls_sag_weights* w, int32_t max_
     lsrg::build_rows_tape_kernel<<<256, 256, 0, st>>>(L.sa_out_wt, D, D, base + s->off_out);
     lsrg::build_rows_tape_kernel<<<256, 256, 0, st>>>(L.l1_wt, FF, D, base + s->off_l1);
     lsrg::build_rows_tape_kernel<<<256, 256, 0, st>>>(L.l2_wt, D, FF, base + s->off_l2);
+    sag_cross_fold_kernel<<<dim3(D / 128, D + 1), 128, 0, st>>>(L, s->wct + (size_t)l * D * D, s->bc + (size_t)l * D);
   }
   SAG_CUDA(cudaGetLastError());
   SAG_CUDA(cudaFuncSetAttribute(lsrg::rows_gemm_kernel<lsrg::ARowMajor, lsrg::EpiStore<false>>,
@@ -210,7 +280,7 @@ extern "C" int ls_sag_create(ls_sag** out, const ls_sag_weights* w, int32_t max_
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsrg::SMEM));
   SAG_CUDA(cudaFuncSetAttribute(lsrg::rows_gemm_kernel<lsrg::ARowMajor, lsrg::EpiResLN<true>>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsrg::SMEM));
-  SAG_CUDA(cudaFuncSetAttribute(sag_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T * (D + 1) * (int)sizeof(float)));
+  SAG_CUDA(cudaFuncSetAttribute(sag_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_SMEM));
   *out = s;
   return LS_OK;
 fail:
@@ -226,26 +296,32 @@ extern "C" int ls_sag_decode_tc(ls_sag* s, int32_t B, const float* x, const floa
   if (B > s->max_batch) return ls_fail(nullptr, LS_EINVAL, "ls_sag_decode_tc: batch %d exceeds max_batch %d", B, s->max_batch);
   cudaStream_t st = (cudaStream_t)stream;
   const ls_sag_weights& w = s->w;
-  const int rows = B * T, RT = (rows + 127) / 128;
+  const int rows = B * T, RT = lsrg::row_tiles(rows);
   using namespace lsrg;
-  sag_queries_kernel<<<B, 512, 0, st>>>(w, x, s->X);
-  sag_cross_kernel<<<dim3((B + CA_CLIPS - 1) / CA_CLIPS, w.n_layers), 512, 0, st>>>(w, z, B, s->CA);
+  // LS_SAG_MASK (diagnostic, tools/sag_bench.py): bit i = launch kernel kind i, to time the kinds one by one
+  static const int kmask = getenv("LS_SAG_MASK") ? atoi(getenv("LS_SAG_MASK")) : 0xFF;
+  if (kmask & 1) sag_queries_kernel<<<B, 512, 0, st>>>(w, x, s->X);
+  if (kmask & 2) sag_cross_kernel<<<dim3((B + CA_CLIPS - 1) / CA_CLIPS, D / 128, w.n_layers), 128, 0, st>>>(s->wct, s->bc, z, B, s->CA);
   s->launches += 2;
   for (int l = 0; l < w.n_layers; ++l) {
     const ls_sag_layer& L = w.layer[l];
     const uint8_t* base = s->tape + s->layer_bytes * l;
-    rows_gemm_kernel<<<dim3(RT, 3), NTHREADS, SMEM, st>>>(ARowMajor{s->X, D}, base, rows, D, EpiStore<false>{s->QKV, 3 * D, L.sa_in_b});
-    sag_attn_kernel<<<dim3(B, NH), HD, 0, st>>>(s->QKV, s->O);
-    rows_gemm_kernel<<<dim3(RT, 1), NTHREADS, SMEM, st>>>(
-        ARowMajor{s->O, D}, base + s->off_out, rows, D,
-        EpiResLN<true>{s->X, s->X, L.sa_out_b, L.n1_w, L.n1_b, s->CA + (size_t)l * B * D, T, L.n2_w, L.n2_b});
-    rows_gemm_kernel<<<dim3(RT, 2), NTHREADS, SMEM, st>>>(ARowMajor{s->X, D}, base + s->off_l1, rows, D, EpiStore<true>{s->H, FF, L.l1_b});
-    rows_gemm_kernel<<<dim3(RT, 1), NTHREADS, SMEM, st>>>(
-        ARowMajor{s->H, FF}, base + s->off_l2, rows, FF,
-        EpiResLN<false>{s->X, s->X, L.l2_b, L.n3_w, L.n3_b, nullptr, T, nullptr, nullptr});
+    if (kmask & 4)
+      rows_gemm_kernel<<<dim3(RT, 3), NTHREADS, SMEM, st>>>(ARowMajor{s->X, D}, base, rows, D, EpiStore<false>{s->QKV, 3 * D, L.sa_in_b});
+    if (kmask & 8) sag_attn_kernel<<<dim3(B, NH), HD, 0, st>>>(s->QKV, s->O);
+    if (kmask & 16)
+      rows_gemm_kernel<<<dim3(RT, 1), NTHREADS, SMEM, st>>>(
+          ARowMajor{s->O, D}, base + s->off_out, rows, D,
+          EpiResLN<true>{s->X, s->X, L.sa_out_b, L.n1_w, L.n1_b, s->CA + (size_t)l * B * D, T, L.n2_w, L.n2_b});
+    if (kmask & 32)
+      rows_gemm_kernel<<<dim3(RT, 2), NTHREADS, SMEM, st>>>(ARowMajor{s->X, D}, base + s->off_l1, rows, D, EpiStore<true>{s->H, FF, L.l1_b});
+    if (kmask & 64)
+      rows_gemm_kernel<<<dim3(RT, 1), NTHREADS, SMEM, st>>>(
+          ARowMajor{s->H, FF}, base + s->off_l2, rows, FF,
+          EpiResLN<false>{s->X, s->X, L.l2_b, L.n3_w, L.n3_b, nullptr, T, nullptr, nullptr});
     s->launches += 5;
   }
-  sag_final_kernel<<<B, 256, T * (D + 1) * sizeof(float), st>>>(w, s->X, mask, out);
+  if (kmask & 128) sag_final_kernel<<<B, 256, FIN_SMEM, st>>>(w, s->X, mask, out);
   s->launches += 1;
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_sag_decode_tc: %s", cudaGetErrorString(e));

@@ -234,7 +234,7 @@ int lsw_audio_proj(ls_handle* h, const float* af_cm, int nb, float* A, cudaStrea
   WavTc* wt = static_cast<WavTc*>(h->wavtc);
   if (!wt) return ls_fail(h, LS_EUNSUPPORTED, "tensor-core precompute not initialised");
   const int rows = nb * LS_F;
-  lsrg::rows_gemm_kernel<<<dim3((rows + 127) / 128, 1), lsrg::NTHREADS, lsrg::SMEM, s>>>(
+  lsrg::rows_gemm_kernel<<<dim3(lsrg::row_tiles(rows), 1), lsrg::NTHREADS, lsrg::SMEM, s>>>(
       lsrg::AChanMajor34{af_cm, LS_AF}, wt->tape_a, rows, LS_AF, lsrg::EpiStore<false>{A, LS_D, nullptr});
   LS_LAUNCH_CHECK(h);
   return LS_OK;

@@ -70,7 +70,8 @@ class Decoder_TRANSFORMER(nn.Module):
         self._drop_tc()
 
     def _drop_tc(self):
-        tc, self._tc = getattr(self, "_tc", None), None
+        tc = self.__dict__.get("_tc")
+        self.__dict__["_tc"] = None          # not nn.Module.__setattr__: this also runs at interpreter shutdown
         if tc is not None:
             try:
                 _cabi.load_library().ls_sag_destroy(tc[2])
