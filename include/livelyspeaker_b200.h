@@ -150,6 +150,22 @@ int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t,
                    const float* eps_cond, const float* eps_uncond, const float* scale,
                    float* out, void* stream);
 
+/* The differentiable model call of the *_with_grad samplers (gaussian_diffusion.py:444-505 condition_*_with_grad,
+ * 560-606 p_sample_with_grad, 800-855 ddim_sample_with_grad): there the reference runs p_mean_variance under
+ * torch.enable_grad() with x.requires_grad_(), so that cond_fn(x, t, p_mean_var, **kwargs) can differentiate a function of
+ * p_mean_var['pred_xstart'] with respect to x.
+ *   ls_cfg_forward_grad: ls_cfg_forward on the exact-order fp32 path that also keeps the input of every MLPblock
+ *     (B * 2 * n_layers * S * 512 floats; allocated on first use and grown with the batch - the one exception to
+ *     "no allocation after ls_create").
+ *   ls_cfg_backward: grad_x [B,J*D,F] = J^T grad_out for J = d out / d x of the LAST ls_cfg_forward_grad call of this
+ *     handle (same B; scale = the guidance scales of that call).  The conditioning, the style draws and the weights are
+ *     constants of this derivative; clamping / denoised_fn are the caller's (torch autograd's) business.               */
+int ls_cfg_forward_grad(ls_handle* h, int32_t B, const float* x, const int64_t* t,
+                        const float* eps_cond, const float* eps_uncond, const float* scale,
+                        float* out, void* stream);
+int ls_cfg_backward(ls_handle* h, int32_t B, const float* grad_out, const float* scale,
+                    float* grad_x, void* stream);
+
 /* One denoising step with a batch-uniform timestep: _WrappedModel +
  * ClassifierFreeSampleModel + RAG + p_mean_variance + p_sample / ddim_sample
  * (respace.py:118-130, cfg_sampler.py:24-31, RAG.py:98-133,

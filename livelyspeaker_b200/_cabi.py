@@ -19,7 +19,7 @@ IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
-           "ls_model_forward", "ls_cfg_forward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_sag_create", "ls_sag_decode_tc",
+           "ls_model_forward", "ls_cfg_forward", "ls_cfg_forward_grad", "ls_cfg_backward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_sag_create", "ls_sag_decode_tc",
            "ls_sag_launch_count", "ls_sag_destroy", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
            "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align"]
 
@@ -313,6 +313,30 @@ class Engine:
                                                 c_void_p(eps_c.data_ptr()), c_void_p(eps_u.data_ptr()),
                                                 c_void_p(scale.data_ptr()), c_void_p(out.data_ptr()), _stream()))
         return _ref_layout(out)
+
+    def cfg_forward_grad(self, x, t, eps_c, eps_u, scale):
+        """ls_cfg_forward_grad: cfg_forward on the exact-order fp32 path, keeping what ls_cfg_backward needs."""
+        B = x.shape[0]
+        x = _f32(x, self.device)
+        t = self._timesteps(t, B)
+        eps_c, eps_u, scale = _f32(eps_c, self.device), _f32(eps_u, self.device), _f32(scale, self.device)
+        out = torch.empty(B, self.dims.njoints, self.dims.nfeats, 34, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_cfg_forward_grad(self.h, B, c_void_p(x.data_ptr()), c_void_p(t.data_ptr()),
+                                                     c_void_p(eps_c.data_ptr()), c_void_p(eps_u.data_ptr()),
+                                                     c_void_p(scale.data_ptr()), c_void_p(out.data_ptr()), _stream()))
+        return _ref_layout(out)
+
+    def cfg_backward(self, grad_out, scale):
+        """ls_cfg_backward: J^T grad_out for the last cfg_forward_grad call (J = d out / d x)."""
+        B = grad_out.shape[0]
+        g = _f32(grad_out, self.device)
+        scale = _f32(scale, self.device)
+        gx = torch.empty(B, self.dims.njoints, self.dims.nfeats, 34, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_cfg_backward(self.h, B, c_void_p(g.data_ptr()), c_void_p(scale.data_ptr()),
+                                                 c_void_p(gx.data_ptr()), _stream()))
+        return gx
 
     def step(self, params, x_t, eps_c, eps_u, noise, scale, x_prev, pred_x0):
         """One fused denoising step.  x_t / x_prev / pred_x0: dense fp32 [B,J,D,F] on the

@@ -140,6 +140,8 @@ extern "C" void ls_destroy(ls_handle* h) {
   cudaSetDevice(h->cfg.device);
   lsf_destroy(h);
   lsw_destroy(h);
+  for (void* p : {(void*)h->grad_ckpt, (void*)h->grad_gx, (void*)h->grad_t})
+    if (p) cudaFree(p);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
 }
@@ -333,6 +335,45 @@ extern "C" int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int
   }
   if ((rc = lsk_denoise_simt(h, B, x, t, -1, 3, eps_cond, eps_uncond, h->out_c, h->out_u, s))) return rc;
   return lsk_cfg_combine(h, B, h->out_c, h->out_u, scale, out, s);
+}
+
+// ---- differentiable denoiser call (the *_with_grad samplers) ------------------------------------------------------
+static int grad_workspace(ls_handle* h, int B) {
+  if (B <= h->grad_cap) return LS_OK;
+  for (void* p : {(void*)h->grad_ckpt, (void*)h->grad_gx, (void*)h->grad_t})
+    if (p) cudaFree(p);
+  h->grad_ckpt = nullptr; h->grad_gx = nullptr; h->grad_t = nullptr; h->grad_cap = 0;
+  const size_t ck = (size_t)B * 2 * h->cfg.n_layers * h->S * LS_D * sizeof(float);
+  if (cudaMalloc(&h->grad_ckpt, ck) != cudaSuccess || cudaMalloc(&h->grad_gx, (size_t)2 * B * h->JD * LS_F * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&h->grad_t, (size_t)B * sizeof(int64_t)) != cudaSuccess)
+    return ls_fail(h, LS_ENOMEM, "ls_cfg_forward_grad: %zu bytes of checkpoints for batch %d", ck, B);
+  h->grad_cap = B;
+  return LS_OK;
+}
+
+extern "C" int ls_cfg_forward_grad(ls_handle* h, int32_t B, const float* x, const int64_t* t, const float* eps_cond,
+                                   const float* eps_uncond, const float* scale, float* out, void* stream) {
+  int rc = check_ready(h, B, true);
+  if (rc) return rc;
+  if (!x || !t || !eps_cond || !eps_uncond || !scale || !out) return ls_fail(h, LS_EINVAL, "null argument");
+  if ((rc = grad_workspace(h, B))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  LS_CUDA(h, cudaMemcpyAsync(h->grad_t, t, (size_t)B * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if ((rc = lsk_denoise_simt(h, B, x, t, -1, 3, eps_cond, eps_uncond, h->out_c, h->out_u, s, h->grad_ckpt))) return rc;
+  h->grad_batch = B;
+  return lsk_cfg_combine(h, B, h->out_c, h->out_u, scale, out, s);
+}
+
+extern "C" int ls_cfg_backward(ls_handle* h, int32_t B, const float* grad_out, const float* scale, float* grad_x,
+                               void* stream) {
+  int rc = check_ready(h, B, true);
+  if (rc) return rc;
+  if (!grad_out || !scale || !grad_x) return ls_fail(h, LS_EINVAL, "null argument");
+  if (h->grad_batch != B) return ls_fail(h, LS_ESTATE, "ls_cfg_backward: no saved forward for batch %d (last: %d)", B, h->grad_batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = lsk_denoise_simt_bwd(h, B, h->grad_t, h->grad_ckpt, grad_out, scale, h->grad_gx, s))) return rc;
+  const int64_t n = (int64_t)B * h->JD * LS_F;
+  return lsk_axpby(h, n, h->grad_gx, h->grad_gx + n, 1.f, 1.f, grad_x, s);
 }
 
 static_assert(sizeof(ls_step_params) == 48 && sizeof(ls_step_io) == 64 && offsetof(ls_step_io, x_prev) == 48,

@@ -79,6 +79,11 @@ struct ls_handle {
   int wav_chunk = 0;
   float* dbg_h = nullptr;   // ls_debug_hidden target (nullptr = off)
   int dbg_layer = -2;
+  // ls_cfg_forward_grad / ls_cfg_backward (allocated on first use, grown with the batch)
+  float* grad_ckpt = nullptr;   // [B][2][n_layers][S][512]
+  float* grad_gx = nullptr;     // [2][B][JD][34]
+  int64_t* grad_t = nullptr;    // [B] timesteps of the saved forward
+  int grad_cap = 0, grad_batch = 0;
   void* fused = nullptr;    // state of the tcgen05 path (ls_fused.cu)
   void* wavtc = nullptr;    // state of the tcgen05 WavEncoder convolutions (ls_wavenc_tc.cu)
 };
@@ -109,8 +114,12 @@ int lsk_time_embed_table(ls_handle* h, const float* pe, const float* w1, const f
 int lsk_transpose(ls_handle* h, const float* in, float* out, int rows, int cols, int ld_in, cudaStream_t s);
 int lsk_cm_to_fm(ls_handle* h, const float* in_cm, float* out_fm, int B, cudaStream_t s);
 // ls_denoise_simt.cu
+// ckpt (or nullptr): [B][2 passes][n_layers][S][512] inputs of every MLPblock, for lsk_denoise_simt_bwd
 int lsk_denoise_simt(ls_handle* h, int B, const float* x, const int64_t* t, int t_uniform, int pass_mask,
-                     const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s);
+                     const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s,
+                     float* ckpt = nullptr);
+int lsk_denoise_simt_bwd(ls_handle* h, int B, const int64_t* t, const float* ckpt, const float* grad_out,
+                         const float* scale, float* gx, cudaStream_t s);
 // ls_update.cu
 int lsk_cfg_combine(ls_handle* h, int B, const float* out_c, const float* out_u, const float* scale,
                     float* out, cudaStream_t s);

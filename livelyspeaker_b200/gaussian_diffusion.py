@@ -6,9 +6,11 @@ attribute tables) for the SAMPLING path: schedules (:26-70), derived fp64 tables
 p_mean_variance (:284-399), p_sample (:507-558), p_sample_loop[_progressive]
 (:608-743), ddim_sample (:745-798), ddim_sample_loop[_progressive] (:895-1014),
 condition_mean / condition_score (:429-481), plms_sample[_loop] (:1016-1211),
-_extract_into_tensor (:1651-1664).  Training losses, VLB terms and the *_with_grad
-samplers (they need autograd through the denoiser) are outside the hot path
- and raise NotImplementedError.
+_extract_into_tensor (:1651-1664), and the *_with_grad samplers (:444-505, :560-606,
+:800-855) whose model call is differentiable with respect to x through a hand-written
+backward kernel (ls_cfg_forward_grad / ls_cfg_backward).  Training losses and VLB terms
+need gradients with respect to the weights: outside the hot path,
+they raise NotImplementedError.
 
 Two execution routes:
   * fused  - the model is this package's ClassifierFreeSampleModel(RAG) and no Python
@@ -369,6 +371,55 @@ class GaussianDiffusion:
         out["mean"], _, _ = self.q_posterior_mean_variance(x_start=out["pred_xstart"], x_t=x, t=t)
         return out
 
+    def condition_mean_with_grad(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        # gaussian_diffusion.py:444-456: cond_fn sees the SPACED t and the p_mean_variance dict (still attached to x)
+        gradient = cond_fn(x, t, p_mean_var, **model_kwargs)
+        return p_mean_var["mean"].float() + p_mean_var["variance"] * gradient.float()
+
+    def condition_score_with_grad(self, cond_fn, p_mean_var, x, t, model_kwargs=None):
+        # gaussian_diffusion.py:483-505
+        alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
+        eps = self._predict_eps_from_xstart(x, t, p_mean_var["pred_xstart"])
+        eps = eps - (1 - alpha_bar).sqrt() * cond_fn(x, t, p_mean_var, **model_kwargs)
+        out = p_mean_var.copy()
+        out["pred_xstart"] = self._predict_xstart_from_eps(x, t, eps)
+        out["mean"], _, _ = self.q_posterior_mean_variance(x_start=out["pred_xstart"], x_t=x, t=t)
+        return out
+
+    def p_sample_with_grad(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None):
+        """gaussian_diffusion.py:560-606.  p_mean_variance runs under enable_grad on x.requires_grad_(): for this
+        package's CFG wrapper the model call is an autograd node backed by ls_cfg_forward_grad / ls_cfg_backward."""
+        with th.enable_grad():
+            x = x.detach().requires_grad_()
+            out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                       model_kwargs=model_kwargs)
+            noise = self.noise_source.randn_like(x)
+            nonzero_mask = (t != 0).float().view(-1, *([1] * (len(x.shape) - 1)))
+            if cond_fn is not None:
+                out["mean"] = self.condition_mean_with_grad(cond_fn, out, x, t, model_kwargs=model_kwargs)
+        sample = out["mean"] + nonzero_mask * th.exp(0.5 * out["log_variance"]) * noise
+        return {"sample": sample, "pred_xstart": out["pred_xstart"].detach()}
+
+    def ddim_sample_with_grad(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                              eta=0.0):
+        """gaussian_diffusion.py:800-855."""
+        with th.enable_grad():
+            x = x.detach().requires_grad_()
+            out_orig = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                            model_kwargs=model_kwargs)
+            out = out_orig if cond_fn is None else self.condition_score_with_grad(cond_fn, out_orig, x, t,
+                                                                                  model_kwargs=model_kwargs)
+        out["pred_xstart"] = out["pred_xstart"].detach()
+        eps = self._predict_eps_from_xstart(x, t, out["pred_xstart"])
+        alpha_bar = _extract_into_tensor(self.alphas_cumprod, t, x.shape)
+        alpha_bar_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, x.shape)
+        sigma = eta * th.sqrt((1 - alpha_bar_prev) / (1 - alpha_bar)) * th.sqrt(1 - alpha_bar / alpha_bar_prev)
+        noise = self.noise_source.randn_like(x)
+        mean_pred = out["pred_xstart"] * th.sqrt(alpha_bar_prev) + th.sqrt(1 - alpha_bar_prev - sigma ** 2) * eps
+        nonzero_mask = (t != 0).float().view(-1, *([1] * (len(x.shape) - 1)))
+        sample = mean_pred + nonzero_mask * sigma * noise
+        return {"sample": sample, "pred_xstart": out_orig["pred_xstart"].detach()}
+
     def p_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
                  const_noise=False):
         out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
@@ -448,8 +499,11 @@ class GaussianDiffusion:
     def _sample_loop_progressive(self, ddim, model, shape, noise, clip_denoised, denoised_fn, cond_fn,
                                  model_kwargs, device, progress, eta, skip_timesteps, init_image,
                                  randomize_class, cond_fn_with_grad, const_noise, chunk=1):
-        if cond_fn_with_grad:
-            raise NotImplementedError("*_with_grad samplers are outside the sampling hot path (SURVEY.md 8f)")
+        if cond_fn_with_grad and const_noise:
+            # the reference's loops pass const_noise= to the *_with_grad samplers, which do not accept it (TypeError for
+            # EVERY cond_fn_with_grad call, gaussian_diffusion.py:733 / :1010); here the loops work unless const_noise
+            # is actually requested
+            raise TypeError("the *_with_grad samplers got an unexpected keyword argument 'const_noise'")
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
@@ -478,7 +532,17 @@ class GaussianDiffusion:
                     model_kwargs['y'] = th.randint(low=0, high=model.num_classes, size=model_kwargs['y'].shape,
                                                    device=model_kwargs['y'].device)
                 with th.no_grad():
-                    if ddim:
+                    if cond_fn_with_grad:
+                        if ddim:
+                            out = self.ddim_sample_with_grad(model, img, t, clip_denoised=clip_denoised,
+                                                             denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                                             model_kwargs=model_kwargs, eta=eta)
+                        else:
+                            out = self.p_sample_with_grad(model, img, t, clip_denoised=clip_denoised,
+                                                          denoised_fn=denoised_fn, cond_fn=cond_fn,
+                                                          model_kwargs=model_kwargs)
+                        out = {"sample": out["sample"].detach(), "pred_xstart": out["pred_xstart"]}
+                    elif ddim:
                         out = self.ddim_sample(model, img, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
                                                cond_fn=cond_fn, model_kwargs=model_kwargs, eta=eta,
                                                const_noise=const_noise)
@@ -707,5 +771,5 @@ class GaussianDiffusion:
                                   "(SURVEY.md section 8f)")
 
     training_losses = _out_of_scope
-    p_sample_with_grad = ddim_sample_with_grad = ddim_reverse_sample = _out_of_scope
+    ddim_reverse_sample = _out_of_scope
     calc_bpd_loop = _vb_terms_bpd = _prior_bpd = _out_of_scope

@@ -132,6 +132,57 @@ def ddim_step(sd, tab, tmap, x, i, y, tape, nj, nf, eta=0.0, clip_denoised=False
     return mean + nz * sigma * noise, x0_ret
 
 
+def _p_mean_var_grad(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised, hooks=None):
+    """p_mean_variance under enable_grad with x.requires_grad_() (gaussian_diffusion.py:590-599, 819-828): the dict the
+    reference hands to cond_fn(x, t, p_mean_var, **model_kwargs), still attached to x's autograd graph."""
+    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised, hooks)
+    mean = _pick(tab["posterior_mean_coef1"], i) * x0 + _pick(tab["posterior_mean_coef2"], i) * x
+    shape = x.shape
+    return {"mean": mean, "variance": _pick(tab["posterior_variance"], i).expand(shape),
+            "log_variance": _pick(tab["posterior_log_variance_clipped"], i).expand(shape), "pred_xstart": x0}
+
+
+def p_sample_with_grad_step(sd, tab, tmap, x, i, y, tape, nj, nf, cond_fn, clip_denoised=False, hooks=None):
+    """p_sample_with_grad + condition_mean_with_grad (gaussian_diffusion.py:560-606, 444-456).  cond_fn is called with
+    the SPACED index tensor (SpacedDiffusion wraps condition_mean / condition_score only, respace.py:100-104) and may
+    differentiate p_mean_var with respect to x.  Returns (sample, pred_xstart)."""
+    t = torch.full((x.shape[0],), i, dtype=torch.long)
+    with torch.enable_grad():
+        x = x.detach().requires_grad_()
+        out = _p_mean_var_grad(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised, hooks)
+        noise = tape.draw_like(x)
+        mean = out["mean"]
+        if cond_fn is not None:
+            mean = mean.float() + out["variance"] * cond_fn(x, t, out, y=y).float()
+    nz = 0.0 if i == 0 else 1.0
+    sample = mean + nz * torch.exp(0.5 * out["log_variance"]) * noise
+    return sample.detach(), out["pred_xstart"].detach()
+
+
+def ddim_sample_with_grad_step(sd, tab, tmap, x, i, y, tape, nj, nf, cond_fn, eta=0.0, clip_denoised=False, hooks=None):
+    """ddim_sample_with_grad + condition_score_with_grad (gaussian_diffusion.py:800-855, 483-505)."""
+    t = torch.full((x.shape[0],), i, dtype=torch.long)
+    recip, recipm1 = _pick(tab["sqrt_recip_alphas_cumprod"], i), _pick(tab["sqrt_recipm1_alphas_cumprod"], i)
+    ab, ab_prev = _pick(tab["alphas_cumprod"], i), _pick(tab["alphas_cumprod_prev"], i)
+    with torch.enable_grad():
+        x = x.detach().requires_grad_()
+        out = _p_mean_var_grad(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised, hooks)
+        x0_orig = out["pred_xstart"]
+        x0 = x0_orig
+        if cond_fn is not None:
+            eps = (recip * x - x0) / recipm1
+            eps = eps - (1 - ab).sqrt() * cond_fn(x, t, out, y=y)
+            x0 = recip * x - recipm1 * eps
+    x0 = x0.detach()
+    x = x.detach()
+    eps = (recip * x - x0) / recipm1
+    sigma = eta * torch.sqrt((1 - ab_prev) / (1 - ab)) * torch.sqrt(1 - ab / ab_prev)
+    noise = tape.draw_like(x)
+    mean = x0 * torch.sqrt(ab_prev) + torch.sqrt(1 - ab_prev - sigma ** 2) * eps
+    nz = 0.0 if i == 0 else 1.0
+    return mean + nz * sigma * noise, x0_orig.detach()
+
+
 def sample_loop(sd, tab, tmap, shape, y, tape, ddim=False, eta=0.0, clip_denoised=False,
                 skip_timesteps=0, init_image=None, const_noise=False, noise=None, trace=None, hooks=None,
                 const_noise_init=True):

@@ -59,5 +59,11 @@ def golden_hooks():
 
 
 @pytest.fixture(scope="session")
+def golden_grad():
+    return {"ted": dict(np.load(os.path.join(GOLDEN, "grad_ted.npz"))),
+            "beat": dict(np.load(os.path.join(GOLDEN, "grad_beat.npz")))}
+
+
+@pytest.fixture(scope="session")
 def golden_metrics():
     return dict(np.load(os.path.join(GOLDEN, "metrics.npz")))

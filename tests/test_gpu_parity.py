@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle
 on the same seeded inputs / recorded noise and against the committed reference fixtures.
 Tolerance = BASELINE.json north_star: rtol 1e-3, atol 1e-4 (fp32)."""
+import os
+import sys
 import types
 
 import numpy as np
@@ -788,3 +790,126 @@ def test_rhythm_metric_on_device(golden_metrics):
     assert (mask_dev.cpu() != o["beat_mask"]).sum() <= max(2, int(0.01 * o["beat_mask"].sum()))
     with pytest.raises(ls.LsError):
         metrics.motion_beats(out.cpu())
+
+
+# ---- *_with_grad samplers: differentiable model call = ls_cfg_forward_grad / ls_cfg_backward -------------------------
+def _grad_cases():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import grad_cases
+    return grad_cases
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_cfg_backward_vjp_vs_reference_autograd(name, golden_grad):
+    """J^T g of ClassifierFreeSampleModel(RAG) with respect to x: the hand-written backward kernel against torch
+    autograd through the REFERENCE modules (fixture) and against autograd through the oracle; per-clip timesteps."""
+    gold = golden_grad[name]
+    dims, sd, cfg, _ = build(name, "")
+    Bv = gold["vjp_x"].shape[0]
+    y = synthetic.synth_cond(dims, Bv, device=DEV)
+    x = torch.from_numpy(gold["vjp_x"]).to(DEV).requires_grad_()
+    gout = torch.from_numpy(gold["vjp_gout"]).to(DEV)
+    cfg.noise_source = ls.ReplayNoise([torch.from_numpy(gold["vjp_eps_c"]), torch.from_numpy(gold["vjp_eps_u"])])
+    t = torch.from_numpy(gold["vjp_t"]).to(DEV)
+    pred = cfg(x, t, y=y)
+    assert pred.requires_grad
+    (gx,) = torch.autograd.grad((pred * gout).sum(), x)
+    _close(pred, gold["vjp_pred"])
+    scale = float(np.abs(gold["vjp_gx"]).max())
+    _close(gx, gold["vjp_gx"], atol=ATOL * max(1.0, scale))
+    # oracle autograd on the same inputs
+    xo = torch.from_numpy(gold["vjp_x"]).requires_grad_()
+    po = rag_oracle.cfg_forward(sd, xo, t.cpu(), synthetic.synth_cond(dims, Bv), torch.from_numpy(gold["vjp_eps_c"]),
+                                torch.from_numpy(gold["vjp_eps_u"]), dims.njoints, dims.nfeats)
+    (gxo,) = torch.autograd.grad((po * gout.cpu()).sum(), xo)
+    _close(gx, gxo, atol=ATOL * max(1.0, scale))
+    # linearity of the VJP in grad_out, and a second backward through a stale graph is refused
+    pred2 = cfg.model.engine(Bv)      # noqa: F841 (engine unchanged)
+    cfg.noise_source = ls.ReplayNoise([torch.from_numpy(gold["vjp_eps_c"]), torch.from_numpy(gold["vjp_eps_u"])] * 2)
+    p1 = cfg(x, t, y=y)
+    p2 = cfg(x, t, y=y)
+    with pytest.raises(RuntimeError):
+        torch.autograd.grad((p1 * gout).sum(), x)
+    (g2,) = torch.autograd.grad((p2 * (2.0 * gout)).sum(), x)
+    _close(g2, 2.0 * gold["vjp_gx"], atol=2 * ATOL * max(1.0, scale))
+    # without requires_grad the ordinary (fused) call runs and returns a plain tensor
+    cfg.noise_source = ls.ReplayNoise([torch.from_numpy(gold["vjp_eps_c"]), torch.from_numpy(gold["vjp_eps_u"])])
+    with torch.no_grad():
+        assert not cfg(x.detach(), t, y=y).requires_grad
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+@pytest.mark.parametrize("tag", ["anc_hi", "anc_lo_clip", "ddim_mid", "ddim_eta_lo", "anc_nocond"])
+def test_with_grad_samplers_vs_reference_fixtures(name, tag, golden_grad):
+    """p_sample_with_grad / ddim_sample_with_grad (+ condition_mean_with_grad / condition_score_with_grad) chained over
+    a few steps with a cond_fn that differentiates pred_xstart with respect to x: against the reference's own outputs
+    (tests/golden/make_golden_grad.py) and the oracle, on the recorded draws."""
+    gc = _grad_cases()
+    spec, ddim, seed, i0, n, kw = gc.CASES[tag]
+    dims, sd, cfg, diffusion = build(name, spec)
+    B = 2
+    shape = (B, dims.njoints, dims.nfeats, 34)
+    cond_fn, _ = gc.make_cond_fn(dims, B)
+    cf = None if kw.get("no_cond_fn") else cond_fn
+    tab, tmap = schedule_oracle.build("cosine", 1000, spec)
+    tape = sampler_oracle.NoiseTape(seed=seed)
+    yo = synthetic.synth_cond(dims, B)
+    xo = tape.draw(*shape)
+    want_x, want_x0 = [], []
+    for k in range(n):
+        if ddim:
+            xo, x0o = sampler_oracle.ddim_sample_with_grad_step(sd, tab, tmap, xo, i0 - k, yo, tape, dims.njoints,
+                                                                dims.nfeats, cf, eta=kw.get("eta", 0.0),
+                                                                clip_denoised=kw.get("clip_denoised", False))
+        else:
+            xo, x0o = sampler_oracle.p_sample_with_grad_step(sd, tab, tmap, xo, i0 - k, yo, tape, dims.njoints,
+                                                             dims.nfeats, cf, clip_denoised=kw.get("clip_denoised", False))
+        want_x.append(xo)
+        want_x0.append(x0o)
+    diffusion.noise_source = cfg.noise_source = ls.ReplayNoise(tape.record)
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    x = diffusion.noise_source.randn(shape, DEV)
+    for k in range(n):
+        t = torch.tensor([i0 - k] * B, device=DEV)
+        with torch.no_grad():
+            if ddim:
+                r = diffusion.ddim_sample_with_grad(cfg, x, t, clip_denoised=kw.get("clip_denoised", False), cond_fn=cf,
+                                                    model_kwargs={"y": y}, eta=kw.get("eta", 0.0))
+            else:
+                r = diffusion.p_sample_with_grad(cfg, x, t, clip_denoised=kw.get("clip_denoised", False), cond_fn=cf,
+                                                 model_kwargs={"y": y})
+        assert not r["pred_xstart"].requires_grad
+        x = r["sample"].detach()
+        _close(x, golden_grad[name]["chain_%s_samples" % tag][k])
+        _close(r["pred_xstart"], golden_grad[name]["chain_%s_x0" % tag][k])
+        _close(x, want_x[k])
+        _close(r["pred_xstart"], want_x0[k])
+    assert diffusion.noise_source.pos == len(tape.record)
+
+
+def test_loops_with_cond_fn_with_grad():
+    """p_sample_loop / ddim_sample_loop(cond_fn_with_grad=True): the reference's loops die with a TypeError (they pass
+    const_noise= to samplers that do not take it); here they run the *_with_grad samplers - equal to chaining them by
+    hand - and refuse only an actual const_noise request."""
+    gc = _grad_cases()
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    B = 2
+    shape = (B, 9, 3, 34)
+    cond_fn, _ = gc.make_cond_fn(dims, B)
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    for ddim in (False, True):
+        fn = diffusion.ddim_sample_loop if ddim else diffusion.p_sample_loop
+        torch.manual_seed(11)
+        got = fn(cfg, shape, clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=97, cond_fn=cond_fn,
+                 cond_fn_with_grad=True)
+        torch.manual_seed(11)
+        x = torch.randn(*shape, device=DEV)
+        x = diffusion.q_sample(torch.zeros_like(x), torch.tensor([2] * B, device=DEV), x)   # skip_timesteps without init_image
+        for i in (2, 1, 0):
+            t = torch.tensor([i] * B, device=DEV)
+            step = diffusion.ddim_sample_with_grad if ddim else diffusion.p_sample_with_grad
+            x = step(cfg, x, t, clip_denoised=False, cond_fn=cond_fn, model_kwargs={"y": y})["sample"].detach()
+        assert torch.equal(got, x)
+        with pytest.raises(TypeError):
+            fn(cfg, shape, clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=97, cond_fn=cond_fn,
+               cond_fn_with_grad=True, const_noise=True)

@@ -258,3 +258,29 @@ def test_rhythm_metric_oracle(golden_metrics):
     assert list(g["mean_dir_vec"]) == metrics.MEAN_DIR_VEC and [tuple(p) for p in g["angle_pair"]] == metrics.ANGLE_PAIR
     assert list(g["change_angle"]) == metrics.CHANGE_ANGLE and float(g["thres"]) == metrics.THRES
     assert float(g["sigma"]) == metrics.SIGMA
+
+
+@pytest.mark.parametrize("tag", ["anc_lo_clip", "ddim_eta_lo"])
+def test_oracle_with_grad_samplers_vs_reference_fixture(tag):
+    """The oracle's p_sample_with_grad / ddim_sample_with_grad restatement (autograd through the oracle's denoiser)
+    against the reference's outputs (tests/golden/make_golden_grad.py), TED."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import grad_cases
+    gold = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grad_ted.npz")))
+    spec, ddim, seed, i0, n, kw = grad_cases.CASES[tag]
+    dims = synthetic.TED
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    tab, tmap = schedule_oracle.build("cosine", 1000, spec)
+    cond_fn, _ = grad_cases.make_cond_fn(dims, 2)
+    tape = sampler_oracle.NoiseTape(seed=seed)
+    y = synthetic.synth_cond(dims, 2)
+    x = tape.draw(2, dims.njoints, dims.nfeats, 34)
+    for k in range(n):
+        step = sampler_oracle.ddim_sample_with_grad_step if ddim else sampler_oracle.p_sample_with_grad_step
+        extra = {"eta": kw.get("eta", 0.0)} if ddim else {}
+        x, x0 = step(sd, tab, tmap, x, i0 - k, y, tape, dims.njoints, dims.nfeats, cond_fn,
+                     clip_denoised=kw.get("clip_denoised", False), **extra)
+        np.testing.assert_allclose(x.numpy(), gold["chain_%s_samples" % tag][k], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(x0.numpy(), gold["chain_%s_x0" % tag][k], rtol=RTOL, atol=ATOL)
