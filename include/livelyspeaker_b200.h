@@ -144,6 +144,14 @@ int ls_model_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t,
                      int32_t uncond, const float* style_eps, float* out,
                      float* z_mu, float* z_logvar, void* stream);
 
+/* RAG.forward in TRAINING mode (scripts/model/RAG.py:80-96, 98-133): like ls_model_forward, with the per-clip condition
+ * dropout of mask_cond - cond_drop [B] bytes on the device, 1 = this clip's audio embedding is replaced by zeros (the
+ * caller draws the Bernoulli mask, keeping torch's generator order), NULL = no dropout.  Exact-order fp32 path.
+ * Forward only: gradients with respect to the weights are not built.                           */
+int ls_model_forward_train(ls_handle* h, int32_t B, const float* x, const int64_t* t,
+                           const uint8_t* cond_drop, const float* style_eps, float* out,
+                           float* z_mu, float* z_logvar, void* stream);
+
 /* ClassifierFreeSampleModel.forward (scripts/model/cfg_sampler.py:24-31):
  * out = out_u + scale[b] * (out_c - out_u).                                       */
 int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t,
@@ -272,6 +280,14 @@ int ls_motion_beats(int32_t B, int32_t njoints, int32_t n_frames, const float* s
 int ls_beat_align(int32_t B, int32_t n_frames, const uint8_t* beat_mask, const float* audio_beats,
                   const int32_t* n_audio, int32_t M, float fps, float sigma, double* clip_score,
                   int32_t* clip_n_motion, int32_t* clip_n_audio, int32_t device, void* stream);
+
+/* Loss terms of GaussianDiffusion.training_losses, HUBER branch (scripts/diffusion/gaussian_diffusion.py:21-24,
+ * 1379-1391): target / output are dense [rows][n_frames] (rows = B * njoints * nfeats), z_mu / z_logvar n_z elements
+ * (may both be NULL).  terms (device) receives {rot_mse, vel_mse, kld}: compute_huber of the samples, compute_huber of
+ * their frame differences, -0.5 * mean(1 + logvar - mu^2 - exp(logvar)).  Stateless; errors through ls_last_error(NULL). */
+int ls_huber_terms(int64_t rows, int32_t n_frames, const float* target, const float* output,
+                   int64_t n_z, const float* z_mu, const float* z_logvar, float* terms,
+                   int32_t device, void* stream);
 
 /* Introspection used by tests / bench: number of kernels launched by this handle
  * since creation, and read-back of the step-invariant buffers.                    */

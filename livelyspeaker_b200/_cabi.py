@@ -19,7 +19,7 @@ IMPL_NAMES = {"auto": 0, "simt": 1, "tc_bf16x3": 2, "tc_bf16": 3}
 
 EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_load_weight",
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
-           "ls_model_forward", "ls_cfg_forward", "ls_cfg_forward_grad", "ls_cfg_backward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_sag_create", "ls_sag_decode_tc",
+           "ls_model_forward", "ls_model_forward_train", "ls_huber_terms", "ls_cfg_forward", "ls_cfg_forward_grad", "ls_cfg_backward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_sag_create", "ls_sag_decode_tc",
            "ls_sag_launch_count", "ls_sag_destroy", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
            "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align"]
 
@@ -302,6 +302,23 @@ class Engine:
                                                   c_void_p(lv.data_ptr()), _stream()))
         return _ref_layout(out), mu, lv
 
+    def model_forward_train(self, x, t, cond_drop, style_eps):
+        """ls_model_forward_train: RAG.forward with the training-mode per-clip condition dropout (forward only)."""
+        B = x.shape[0]
+        x = _f32(x, self.device)
+        t = self._timesteps(t, B)
+        eps = _f32(style_eps, self.device)
+        drop = None if cond_drop is None else cond_drop.to(self.device).to(torch.uint8).contiguous()
+        out = torch.empty(B, self.dims.njoints, self.dims.nfeats, 34, dtype=torch.float32, device=self.device)
+        mu = torch.empty(B, 1, self.dims.latent_dim, dtype=torch.float32, device=self.device)
+        lv = torch.empty_like(mu)
+        with torch.cuda.device(self.device):
+            self._check(self.lib.ls_model_forward_train(self.h, B, c_void_p(x.data_ptr()), c_void_p(t.data_ptr()),
+                                                        c_void_p(drop.data_ptr()) if drop is not None else None,
+                                                        c_void_p(eps.data_ptr()), c_void_p(out.data_ptr()),
+                                                        c_void_p(mu.data_ptr()), c_void_p(lv.data_ptr()), _stream()))
+        return _ref_layout(out), mu, lv
+
     def cfg_forward(self, x, t, eps_c, eps_u, scale):
         B = x.shape[0]
         x = _f32(x, self.device)
@@ -403,3 +420,20 @@ class Engine:
             self._check(self.lib.ls_q_sample(self.h, x0.numel(), c_void_p(x0.data_ptr()), c_void_p(noise.data_ptr()),
                                              float(c_x0), float(c_noise), c_void_p(out.data_ptr()), _stream()))
         return out
+
+
+def huber_terms(target, output, z_mu, z_logvar, terms):
+    """ls_huber_terms: {rot_mse, vel_mse, kld} of training_losses' HUBER branch into terms (3 floats on the device)."""
+    lib = load_library()
+    lib.ls_huber_terms.argtypes = [c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int32,
+                                   c_void_p]
+    F = target.shape[-1]
+    rows = target.numel() // F
+    with torch.cuda.device(target.device):
+        rc = lib.ls_huber_terms(rows, F, c_void_p(target.data_ptr()), c_void_p(output.data_ptr()),
+                                0 if z_mu is None else z_mu.numel(),
+                                None if z_mu is None else c_void_p(z_mu.data_ptr()),
+                                None if z_logvar is None else c_void_p(z_logvar.data_ptr()),
+                                c_void_p(terms.data_ptr()), target.device.index or 0, _stream())
+    if rc != 0:
+        raise LsError("libls_b200 error %d: %s" % (rc, lib.ls_last_error(None).decode()))

@@ -319,6 +319,18 @@ extern "C" int ls_model_forward(ls_handle* h, int32_t B, const float* x, const i
   return LS_OK;
 }
 
+extern "C" int ls_model_forward_train(ls_handle* h, int32_t B, const float* x, const int64_t* t, const uint8_t* cond_drop,
+                                      const float* style_eps, float* out, float* z_mu, float* z_logvar, void* stream) {
+  int rc = check_ready(h, B, true);
+  if (rc) return rc;
+  if (!x || !t || !style_eps || !out) return ls_fail(h, LS_EINVAL, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = lsk_denoise_simt(h, B, x, t, -1, 1, style_eps, style_eps, out, out, s, nullptr, cond_drop))) return rc;
+  if (z_mu) LS_CUDA(h, cudaMemcpyAsync(z_mu, h->z_mu, (size_t)B * LS_D * 4, cudaMemcpyDeviceToDevice, s));
+  if (z_logvar) LS_CUDA(h, cudaMemcpyAsync(z_logvar, h->z_lv, (size_t)B * LS_D * 4, cudaMemcpyDeviceToDevice, s));
+  return LS_OK;
+}
+
 extern "C" int ls_cfg_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t, const float* eps_cond,
                               const float* eps_uncond, const float* scale, float* out, void* stream) {
   int rc = check_ready(h, B, true);

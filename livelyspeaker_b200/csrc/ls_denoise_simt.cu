@@ -51,14 +51,16 @@ denoise_simt_kernel(LsWeights w, int JD, int n_layers, int pass_mask, const floa
                     const float* __restrict__ P, const float* __restrict__ z_mu, const float* __restrict__ z_lv,
                     const float* __restrict__ emo_tok, const float* __restrict__ eps_c,
                     const float* __restrict__ eps_u, float* __restrict__ out_c, float* __restrict__ out_u,
-                    float* __restrict__ dbg_h, int dbg_layer, float* __restrict__ ckpt) {
+                    float* __restrict__ dbg_h, int dbg_layer, float* __restrict__ ckpt,
+                    const uint8_t* __restrict__ cond_drop) {
   constexpr int NPRE = S - LS_F;
   extern __shared__ float sm[];
   float* hs = sm;                 // [S][512] residual stream
   float* us = hs + S * LS_D;      // [S][512] LN output / staging
   float* wt = us + S * LS_D;      // [S][S] token-mix weight, then [S] bias
   const int b = blockIdx.x, c = threadIdx.x;
-  const bool uncond = (pass_mask == 3) ? (blockIdx.y == 1) : (pass_mask == 2);
+  // cond_drop (training-mode mask_cond, RAG.py:84-93): clips whose audio embedding is replaced by zeros
+  const bool uncond = ((pass_mask == 3) ? (blockIdx.y == 1) : (pass_mask == 2)) || (cond_drop != nullptr && cond_drop[b] != 0);
   const float* eps = uncond ? eps_u : eps_c;
   float* out = uncond ? out_u : out_c;
 
@@ -172,22 +174,24 @@ denoise_simt_kernel(LsWeights w, int JD, int n_layers, int pass_mask, const floa
 
 template <int S>
 static int launch_simt(ls_handle* h, int B, const float* x, const int64_t* t, int t_uniform, int pass_mask,
-                       const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s, float* ckpt) {
+                       const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s, float* ckpt,
+                       const uint8_t* cond_drop) {
   const size_t smem = (size_t)(2 * S * LS_D + S * S + S) * sizeof(float);
   // the attribute is per DEVICE: set on every launch (one process may drive several GPUs)
   LS_CUDA(h, cudaFuncSetAttribute(denoise_simt_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(B, pass_mask == 3 ? 2 : 1);
   denoise_simt_kernel<S><<<grid, 512, smem, s>>>(h->w, h->JD, h->cfg.n_layers, pass_mask, x, t, t_uniform, h->A, h->P,
                                                  h->z_mu, h->z_lv, h->emo_tok, eps_c, eps_u, out_c, out_u, h->dbg_h,
-                                                 h->dbg_layer, ckpt);
+                                                 h->dbg_layer, ckpt, cond_drop);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
 }
 
 int lsk_denoise_simt(ls_handle* h, int B, const float* x, const int64_t* t, int t_uniform, int pass_mask,
-                     const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s, float* ckpt) {
-  if (h->S == 35) return launch_simt<35>(h, B, x, t, t_uniform, pass_mask, eps_c, eps_u, out_c, out_u, s, ckpt);
-  if (h->S == 36) return launch_simt<36>(h, B, x, t, t_uniform, pass_mask, eps_c, eps_u, out_c, out_u, s, ckpt);
+                     const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s, float* ckpt,
+                     const uint8_t* cond_drop) {
+  if (h->S == 35) return launch_simt<35>(h, B, x, t, t_uniform, pass_mask, eps_c, eps_u, out_c, out_u, s, ckpt, cond_drop);
+  if (h->S == 36) return launch_simt<36>(h, B, x, t, t_uniform, pass_mask, eps_c, eps_u, out_c, out_u, s, ckpt, cond_drop);
   return ls_fail(h, LS_EUNSUPPORTED, "token count %d not built", h->S);
 }
 

@@ -117,7 +117,7 @@ int lsk_cm_to_fm(ls_handle* h, const float* in_cm, float* out_fm, int B, cudaStr
 // ckpt (or nullptr): [B][2 passes][n_layers][S][512] inputs of every MLPblock, for lsk_denoise_simt_bwd
 int lsk_denoise_simt(ls_handle* h, int B, const float* x, const int64_t* t, int t_uniform, int pass_mask,
                      const float* eps_c, const float* eps_u, float* out_c, float* out_u, cudaStream_t s,
-                     float* ckpt = nullptr);
+                     float* ckpt = nullptr, const uint8_t* cond_drop = nullptr);
 int lsk_denoise_simt_bwd(ls_handle* h, int B, const int64_t* t, const float* ckpt, const float* grad_out,
                          const float* scale, float* gx, cudaStream_t s);
 // ls_update.cu

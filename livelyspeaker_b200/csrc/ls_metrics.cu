@@ -154,3 +154,65 @@ extern "C" int ls_beat_align(int32_t B, int32_t n_frames, const uint8_t* beat_ma
   if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_beat_align: %s", cudaGetErrorString(e));
   return LS_OK;
 }
+
+
+// ---- training loss terms: GaussianDiffusion.training_losses, HUBER branch, forward values --------
+// scripts/diffusion/gaussian_diffusion.py:21-24 (compute_huber = smooth_l1(a / 0.1, b / 0.1) * 0.1, mean over all
+// elements), :1379-1391 (rot_mse on the sample, vel_mse on its frame differences, kld of the style posterior).  One
+// block, fixed summation order (deterministic), fp64 accumulation.
+namespace {
+__device__ __forceinline__ double huber01(float a, float b) {
+  const float d = fabsf(a / 0.1f - b / 0.1f);
+  return d < 1.f ? 0.5 * (double)d * (double)d : (double)d - 0.5;
+}
+__global__ void __launch_bounds__(1024) huber_terms_kernel(long long rows, int F, const float* __restrict__ target,
+                                                           const float* __restrict__ output, long long n_z,
+                                                           const float* __restrict__ z_mu, const float* __restrict__ z_lv,
+                                                           float* __restrict__ terms) {
+  __shared__ double red[3][32];
+  double s_rot = 0.0, s_vel = 0.0, s_kld = 0.0;
+  for (long long r = threadIdx.x; r < rows; r += 1024) {
+    const float* tr = target + r * F;
+    const float* orow = output + r * F;
+    float tp = tr[0], op = orow[0];
+    s_rot += huber01(tp, op);
+    for (int f = 1; f < F; ++f) {
+      const float tc = tr[f], oc = orow[f];
+      s_rot += huber01(tc, oc);
+      s_vel += huber01(tc - tp, oc - op);
+      tp = tc;
+      op = oc;
+    }
+  }
+  if (z_mu != nullptr)
+    for (long long i = threadIdx.x; i < n_z; i += 1024) {
+      const float mu = z_mu[i], lv = z_lv[i];
+      s_kld += (double)(1.f + lv - mu * mu - expf(lv));
+    }
+  double v[3] = {s_rot, s_vel, s_kld};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[threadIdx.x][w];
+    const double n = threadIdx.x == 0 ? (double)rows * F : threadIdx.x == 1 ? (double)rows * (F - 1) : (double)n_z;
+    terms[threadIdx.x] = threadIdx.x == 2 ? (float)(-0.5 * t / n) : (float)(0.1 * t / n);
+  }
+}
+}  // namespace
+
+extern "C" int ls_huber_terms(int64_t rows, int32_t n_frames, const float* target, const float* output, int64_t n_z,
+                              const float* z_mu, const float* z_logvar, float* terms, int32_t device, void* stream) {
+  if (rows < 1 || n_frames < 2 || !target || !output || !terms || (z_mu != nullptr) != (z_logvar != nullptr))
+    return ls_fail(nullptr, LS_EINVAL, "ls_huber_terms: bad argument");
+  if (cudaSetDevice(device) != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "cudaSetDevice failed");
+  huber_terms_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(rows, n_frames, target, output, n_z, z_mu, z_logvar, terms);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_huber_terms: %s", cudaGetErrorString(e));
+  return LS_OK;
+}

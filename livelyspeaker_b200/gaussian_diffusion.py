@@ -682,15 +682,25 @@ class GaussianDiffusion:
                     cond_fn_with_grad=False, order=2, old_out=None):
         """Pseudo linear multistep step (gaussian_diffusion.py:1016-1098 of the reference).  Runs on the generic
         route: the denoiser is called through the C ABI (ls_cfg_forward), the multistep algebra is elementwise."""
-        if cond_fn_with_grad:
-            raise NotImplementedError("*_with_grad samplers are outside the sampling hot path (SURVEY.md 8f)")
         if not int(order) or not 1 <= order <= 4:
             raise ValueError('order is invalid (should be int from 1-4).')
 
         def model_eps(x_, t_):
-            orig = self.p_mean_variance(model, x_, t_, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
-                                        model_kwargs=model_kwargs)
-            out_ = orig if cond_fn is None else self.condition_score(cond_fn, orig, x_, t_, model_kwargs=model_kwargs)
+            # gaussian_diffusion.py:1037-1061: with cond_fn_with_grad the model call stays attached to x_ so that
+            # cond_fn(x, t, p_mean_var) can differentiate it (ls_cfg_forward_grad / ls_cfg_backward)
+            with th.set_grad_enabled(bool(cond_fn_with_grad and cond_fn is not None)):
+                x_ = x_.detach().requires_grad_() if cond_fn_with_grad else x_
+                orig = self.p_mean_variance(model, x_, t_, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                            model_kwargs=model_kwargs)
+                if cond_fn is None:
+                    out_ = orig
+                elif cond_fn_with_grad:
+                    out_ = self.condition_score_with_grad(cond_fn, orig, x_, t_, model_kwargs=model_kwargs)
+                    x_ = x_.detach()
+                    out_ = {k: v.detach() for k, v in out_.items()}
+                    orig = {k: v.detach() for k, v in orig.items()}
+                else:
+                    out_ = self.condition_score(cond_fn, orig, x_, t_, model_kwargs=model_kwargs)
             return self._predict_eps_from_xstart(x_, t_, out_["pred_xstart"]), out_, orig
 
         ab_prev = _extract_into_tensor(self.alphas_cumprod_prev, t, x.shape)
@@ -770,6 +780,43 @@ class GaussianDiffusion:
         raise NotImplementedError("training / VLB / *_with_grad are outside the sampling hot path "
                                   "(SURVEY.md section 8f)")
 
-    training_losses = _out_of_scope
+    def training_losses(self, model, x_start, t, model_kwargs=None, noise=None, dataset=None):
+        """gaussian_diffusion.py:1249-1401, LossType.HUBER (what model_util.py:61 configures) - FORWARD VALUES: q_sample,
+        the model in whatever mode it is in (training mode = per-clip condition dropout, ls_model_forward_train), and
+        the loss terms reduced on the device by ls_huber_terms.  The returned tensors carry no autograd graph: the
+        backward pass with respect to the weights (train_loop.py:146-186) is not built."""
+        if self.loss_type != LossType.HUBER:
+            raise NotImplementedError("only LossType.HUBER (model_util.py:61) is built: %s" % self.loss_type)
+        if self.model_mean_type != ModelMeanType.START_X or self.model_var_type not in (ModelVarType.FIXED_SMALL,
+                                                                                         ModelVarType.FIXED_LARGE):
+            raise NotImplementedError("training_losses: START_X with a fixed variance only (model_util.py:42-74)")
+        mask = model_kwargs['y']['mask']            # noqa: F841  (the reference reads it before its None check too)
+        if noise is None:
+            noise = self.noise_source.randn_like(x_start)
+        with th.no_grad():
+            x_t = self.q_sample(x_start, t, noise=noise)
+            all_output = model(x_t, self._scale_timesteps(t), **model_kwargs)
+            model_output = all_output['output']
+            target = x_start
+            assert model_output.shape == target.shape == x_start.shape
+            from . import _cabi
+            dev = model_output.device
+            tgt = _cabi._f32(target, dev)
+            outd = _cabi._f32(model_output, dev)
+            terms_dev = th.empty(3, dtype=th.float32, device=dev)
+            z_mu, z_lv = all_output.get('z_mu'), all_output.get('z_logvar')
+            if z_mu is not None:
+                z_mu, z_lv = _cabi._f32(z_mu, dev), _cabi._f32(z_lv, dev)
+            _cabi.huber_terms(tgt, outd, z_mu, z_lv, terms_dev)
+        terms = {"rot_mse": terms_dev[0]}
+        if self.lambda_vel > 0.:
+            terms["vel_mse"] = terms_dev[1]
+        if z_mu is not None:
+            terms["kld"] = terms_dev[2]
+        terms["loss"] = terms["rot_mse"] + (self.lambda_vel * terms.get('vel_mse', 0.))
+        if not getattr(self, "training_returns_pred", True):      # BEAT tree
+            return terms
+        return terms, {'target': target, 'model_output': model_output}
+
     ddim_reverse_sample = _out_of_scope
     calc_bpd_loop = _vb_terms_bpd = _prior_bpd = _out_of_scope

@@ -54,4 +54,5 @@ def create_gaussian_diffusion(args, timestep_respacing='', variant='ted'):
         diffusion.allow_ddim_const_noise = False
         diffusion.inpaint_noised = False
         diffusion.const_noise_init = False   # scripts_beat/...:700-704: x_T is NOT repeated under const_noise
+        diffusion.training_returns_pred = False   # scripts_beat/...:1388 returns terms only (TED: (terms, pred), :1396-1401)
     return diffusion

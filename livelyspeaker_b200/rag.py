@@ -152,24 +152,32 @@ class RAG(nn.Module):
 
     # ---- forward -----------------------------------------------------------------------
     def mask_cond(self, cond, force_mask=False):
-        """RAG.py:80-96.  Only the sampling (eval) behaviour exists here."""
+        """RAG.py:80-96 (the kernels apply the mask themselves; this mirror is for callers that use it directly)."""
+        bs = cond.shape[0]
         if force_mask:
             return torch.zeros_like(cond)
         if self.training and self.cond_mask_prob > 0.:
-            raise NotImplementedError("training-time condition dropout is outside the sampling path")
+            mask = torch.bernoulli(torch.ones(bs, device=cond.device) * self.cond_mask_prob).view(bs, 1)
+            return (cond.flatten(1) * (1. - mask)).reshape(cond.shape)
         return cond
 
     def forward(self, x, timesteps, y=None):
         """x: [B, njoints, nfeats, 34] (x_t); timesteps: [B] int; y: the cond dict.
         Returns {'output' [B,J,D,34], 'z_mu', 'z_logvar' [B,1,512]} (RAG.py:98-133)."""
-        if self.training and self.cond_mask_prob > 0.:
-            raise NotImplementedError("RAG.forward here implements sampling only: call .eval() first")
         bs, njoints, nfeats, nframes = x.shape
         if (njoints, nfeats, nframes) != (self.njoints, self.nfeats, N_FRAMES):
             raise ValueError("x must be [B,%d,%d,%d]" % (self.njoints, self.nfeats, N_FRAMES))
         eng = self.engine(bs)
         eng.set_cond(y)
         # reparameterize (RAG.py:10-13) draws even in eval mode; keep torch's generator order
+        force_mask = bool(y.get('uncond', False))
+        if self.training and self.cond_mask_prob > 0. and not force_mask:
+            # training mode (RAG.py:84-93): one Bernoulli draw per clip BEFORE the style draw, 1 = null condition.
+            # Forward values only - there is no backward with respect to the weights (SURVEY.md 8f row 4).
+            drop = torch.bernoulli(torch.ones(bs, device=eng.device) * self.cond_mask_prob)
+            eps = torch.randn(bs, 1, self.latent_dim, device=eng.device)
+            out, z_mu, z_logvar = eng.model_forward_train(x, timesteps, drop, eps)
+            return {'output': out, 'z_mu': z_mu, 'z_logvar': z_logvar}
         eps = torch.randn(bs, 1, self.latent_dim, device=eng.device)
-        out, z_mu, z_logvar = eng.model_forward(x, timesteps, bool(y.get('uncond', False)), eps)
+        out, z_mu, z_logvar = eng.model_forward(x, timesteps, force_mask, eps)
         return {'output': out, 'z_mu': z_mu, 'z_logvar': z_logvar}

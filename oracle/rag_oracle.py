@@ -91,6 +91,9 @@ def rag_forward(sd, x, t, y, style_eps, njoints, nfeats, trace=None):
     bs, nj, nf, nframes = x.shape
     af = wav_encoder(sd, y["audio_input"])
     audio_emb = torch.zeros_like(af) if y.get("uncond", False) else af
+    if y.get("cond_drop") is not None and not y.get("uncond", False):
+        # training-mode mask_cond (RAG.py:84-93): 1 = this clip's condition is replaced by zeros
+        audio_emb = (af.flatten(1) * (1.0 - y["cond_drop"].view(bs, 1))).reshape(af.shape)
     ox = y["origin_x"]
     ox[..., N_PRE_SEQ:] = 0
     xi = torch.cat([x, ox], dim=1)

@@ -183,6 +183,29 @@ def ddim_sample_with_grad_step(sd, tab, tmap, x, i, y, tape, nj, nf, cond_fn, et
     return mean + nz * sigma * noise, x0_orig.detach()
 
 
+def training_losses(sd, tab, tmap, x_start, t_idx, y, noise, style_eps, cond_drop, nj, nf, lambda_vel=1.0):
+    """GaussianDiffusion.training_losses, LossType.HUBER (gaussian_diffusion.py:1249-1401): q_sample at the per-clip
+    spaced indices t_idx, RAG.forward in training mode (cond_drop = the Bernoulli mask of mask_cond, RAG.py:84-93;
+    style_eps = reparameterize's draw), compute_huber (:21-24) of the sample and of its frame differences, kld."""
+    import torch.nn.functional as F
+    a = torch.from_numpy(np.asarray(tab["sqrt_alphas_cumprod"]))[t_idx].float().view(-1, 1, 1, 1)
+    b = torch.from_numpy(np.asarray(tab["sqrt_one_minus_alphas_cumprod"]))[t_idx].float().view(-1, 1, 1, 1)
+    x_t = a * x_start + b * noise
+    t_orig = torch.as_tensor(np.asarray(tmap))[t_idx].long()
+    yy = dict(y)
+    yy["cond_drop"] = cond_drop
+    out = rag_oracle.rag_forward(sd, x_t, t_orig, yy, style_eps, nj, nf)
+
+    def huber(p, q):
+        return F.smooth_l1_loss(p / 0.1, q / 0.1) * 0.1
+    o = out["output"]
+    terms = {"rot_mse": huber(x_start, o),
+             "vel_mse": huber(x_start[..., 1:] - x_start[..., :-1], o[..., 1:] - o[..., :-1]),
+             "kld": -0.5 * torch.mean(1 + out["z_logvar"] - out["z_mu"].pow(2) - out["z_logvar"].exp())}
+    terms["loss"] = terms["rot_mse"] + lambda_vel * terms["vel_mse"]
+    return terms, o
+
+
 def sample_loop(sd, tab, tmap, shape, y, tape, ddim=False, eta=0.0, clip_denoised=False,
                 skip_timesteps=0, init_image=None, const_noise=False, noise=None, trace=None, hooks=None,
                 const_noise_init=True):

@@ -65,5 +65,11 @@ def golden_grad():
 
 
 @pytest.fixture(scope="session")
+def golden_train():
+    return {"ted": dict(np.load(os.path.join(GOLDEN, "train_ted.npz"))),
+            "beat": dict(np.load(os.path.join(GOLDEN, "train_beat.npz")))}
+
+
+@pytest.fixture(scope="session")
 def golden_metrics():
     return dict(np.load(os.path.join(GOLDEN, "metrics.npz")))

@@ -195,8 +195,21 @@ def test_plms_loops_ted(tag, golden_plms):
     _close(got, want)
     with pytest.raises(ValueError):
         diffusion.plms_sample(cfg, got, torch.zeros(2, dtype=torch.long, device=DEV), order=5)
-    with pytest.raises(NotImplementedError):
-        diffusion.plms_sample(cfg, got, torch.zeros(2, dtype=torch.long, device=DEV), cond_fn_with_grad=True)
+    # cond_fn_with_grad (gaussian_diffusion.py:1037-1061): a with-grad cond_fn that ignores p_mean_var and t must give
+    # the plain cond_fn result (the model call then runs on the differentiable fp32 path)
+    if tag == "ddim100_o2":
+        y2 = synthetic.synth_cond(dims, 2, device=DEV)
+        tgt = 0.1 * torch.ones_like(got)
+        t5 = torch.full((2,), 5, dtype=torch.long, device=DEV)
+        diffusion.noise_source, cfg.noise_source = ls.TorchNoise(), None
+        torch.manual_seed(3)
+        a = diffusion.plms_sample(cfg, got, t5, clip_denoised=False, model_kwargs={"y": y2},
+                                  cond_fn=lambda x, t, y=None: -(x - tgt))
+        torch.manual_seed(3)
+        b = diffusion.plms_sample(cfg, got, t5, clip_denoised=False, model_kwargs={"y": y2}, cond_fn_with_grad=True,
+                                  cond_fn=lambda x, t, pmv, y=None: -(x - tgt))
+        _close(a["sample"], b["sample"])
+        assert not b["sample"].requires_grad
 
 
 @pytest.mark.parametrize("impl", ["tc", "simt"])
@@ -913,3 +926,52 @@ def test_loops_with_cond_fn_with_grad():
         with pytest.raises(TypeError):
             fn(cfg, shape, clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=97, cond_fn=cond_fn,
                cond_fn_with_grad=True, const_noise=True)
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+@pytest.mark.parametrize("spec", ["", "ddim100"])
+def test_training_losses_forward_vs_reference_fixture(name, spec, golden_train):
+    """GaussianDiffusion.training_losses (HUBER branch) with the model in TRAINING mode (per-clip condition dropout):
+    q_sample, ls_model_forward_train, ls_huber_terms against the reference's own values (make_golden_train.py) and the
+    oracle on the recorded Bernoulli / Gaussian draws.  Forward values only - the terms carry no autograd graph."""
+    gold = golden_train[name]
+    tag = spec or "full"
+    dims = synthetic.dims_for(name)
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    kw = dict(cond_mask_prob=0.5)
+    if name == "ted":
+        model, diffusion = ls.create_model_and_diffusion(_args(**kw), spec)
+    else:
+        model, diffusion = beat_model_util.create_model_and_diffusion(_args(njoints=47, **kw), spec)
+    ls.load_model_wo_clip(model, sd)
+    model = model.to(DEV).train()
+    B = gold["x_start"].shape[0]
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    y["mask"] = torch.ones(B, 34, dtype=torch.bool, device=DEV)
+    x_start = torch.from_numpy(gold["x_start"]).to(DEV)
+    t = torch.from_numpy(gold[tag + "_t"]).to(DEV)
+    noise, drop, eps = (torch.from_numpy(gold[tag + k]).to(DEV) for k in ("_noise", "_drop", "_eps"))
+    o_bern, o_randn = torch.bernoulli, torch.randn
+    torch.bernoulli = lambda *a, **k: drop           # the two draws of RAG.forward in training mode, in their order
+    torch.randn = lambda *a, **k: eps
+    try:
+        res = diffusion.training_losses(model, x_start, t, model_kwargs={"y": y}, noise=noise)
+    finally:
+        torch.bernoulli, torch.randn = o_bern, o_randn
+    terms, pred = res if isinstance(res, tuple) else (res, None)
+    assert (pred is None) == (name == "beat")
+    for k in ("rot_mse", "vel_mse", "kld", "loss"):
+        np.testing.assert_allclose(float(terms[k]), float(gold["%s_%s" % (tag, k)]), rtol=RTOL, atol=ATOL)
+        assert not terms[k].requires_grad
+    if pred is not None:
+        _close(pred["model_output"], gold[tag + "_output"])
+    tab, tmap = schedule_oracle.build("cosine", 1000, spec)
+    ot, oo = sampler_oracle.training_losses(sd, tab, tmap, x_start.cpu(), t.cpu(), synthetic.synth_cond(dims, B),
+                                            noise.cpu(), eps.cpu(), drop.cpu(), dims.njoints, dims.nfeats)
+    for k in ("rot_mse", "vel_mse", "kld", "loss"):
+        np.testing.assert_allclose(float(terms[k]), float(ot[k]), rtol=RTOL, atol=ATOL)
+    # eval mode: no dropout draw, same entry point
+    model.eval()
+    torch.manual_seed(1)
+    r2 = diffusion.training_losses(model, x_start, t, model_kwargs={"y": y}, noise=noise)
+    assert torch.isfinite((r2[0] if isinstance(r2, tuple) else r2)["loss"])

@@ -87,11 +87,22 @@ def test_cfg_wrapper_surface_and_none_quirk():
     assert cfg(torch.zeros(1, 9, 3, 34), torch.zeros(1, dtype=torch.long), y={}) is None
 
 
-def test_training_mode_is_rejected():
-    model, _ = ls.create_model_and_diffusion(_args())
+def test_training_surface_without_a_gpu():
+    """Training mode is a forward-only path since round 2 (ls_model_forward_train / training_losses); like every
+    product path it needs the CUDA engine and fails loudly without one - there is no CPU fallback.  The sampling
+    wrapper still refuses a model in training mode, and non-HUBER losses are not built."""
+    from livelyspeaker_b200 import _cabi
+    model, diffusion = ls.create_model_and_diffusion(_args())
     model.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_cabi.LsError):
         model(torch.zeros(1, 9, 3, 34), torch.zeros(1, dtype=torch.long), {})
+    with pytest.raises(NotImplementedError):
+        ls.ClassifierFreeSampleModel(model)(torch.zeros(1, 9, 3, 34), torch.zeros(1, dtype=torch.long), {})
+    assert hasattr(diffusion, "training_losses") and hasattr(diffusion, "p_sample_with_grad")
+    diffusion.loss_type = ls.gaussian_diffusion.LossType.MSE
+    with pytest.raises(NotImplementedError):
+        diffusion.training_losses(model, torch.zeros(1, 9, 3, 34), torch.zeros(1, dtype=torch.long),
+                                  model_kwargs={"y": {"mask": None}})
 
 
 def test_generic_route_matches_reference_math_with_a_plain_model():
