@@ -79,6 +79,11 @@ constexpr int NSLOT = 4;
 #else
 #define LS_CLUSTER_ATTR
 #endif
+#ifndef LS_LN1_EARLY
+// 1: the channel-mix epilogue of block l adds block l+1's time embedding and accumulates its LayerNorm-1 partial sums
+//    M-tile by M-tile (ln_partial_q), so that only the last butterfly and the 4-warp combine follow the last MMA.
+#define LS_LN1_EARLY 1
+#endif
 #ifndef LS_NOFETCH
 #define LS_NOFETCH 0     // diagnostic: 1 = the producer signals stages without copying (garbage results, pure MMA timing)
 #endif
@@ -238,6 +243,9 @@ __device__ __forceinline__ void butterfly(float* v, int lane) {
   }
 }
 
+template <int CORR>
+__device__ __forceinline__ void ln_finalize_q(uint8_t* sm, int rq, bool use_shift);
+
 // Per-row (sum, sum of squares) over the 512 channels of this group's 18 rows.  `shift` = the previous mean of
 // the row (robust single-pass variance), or 0 when use_shift is false.
 //   CORR == 0: stats[row] = (rstd, -mean * rstd) (normalisation is one FMA; pair layout), means[row] = mean.
@@ -279,6 +287,55 @@ __device__ __forceinline__ void ln_stats_q(const float (&h)[72], uint8_t* sm, in
     butterfly<4>(v, lane);               // lane bits (4 | 3) select (q? | row)
     if ((lane & 7) == 0) part[((warp * NQ) + 16 + ((lane >> 3) & 1)) * 2 + (lane >> 4)] = v[0];
   }
+  ln_finalize_q<CORR>(sm, rq, use_shift);
+}
+
+// One M-tile's share of the NEXT LayerNorm-1 statistics, accumulated into this warp's own partial-sum slots while the
+// tensor pipe still works on the later M-tiles of the channel mix: hm = the thread's 18 rows of channel c_m, already
+// final (+ the next block's time embedding).  Shift = means[] (LayerNorm 2's exact mean of the same rows).  After the
+// last M-tile only ln_finalize_q<0> is left on the critical path - the 4-channel sums, three of the four butterflies
+// and their shuffle latency are off it.  No barrier: a lane only ever touches its own slots.
+template <bool FIRST>
+__device__ __forceinline__ void ln_partial_q(const float* hm, uint8_t* sm, int rq) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* part = reinterpret_cast<float*>(sm + OFF_PART);
+  const float* means = reinterpret_cast<const float*>(sm + OFF_MEAN);
+  const int r0 = NQ * rq;
+  auto row2 = [&](int j, float& s0, float& s1, float& q0, float& q1) {
+    const float2 m2 = *reinterpret_cast<const float2*>(means + r0 + j);
+    const f32x2 d = sub2(pk2(hm[j], hm[j + 1]), pk2(m2.x, m2.y));
+    upk2(d, s0, s1);
+    upk2(mul2(d, d), q0, q1);
+  };
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) row2(8 * g + i, v[i], v[i + 1], v[8 + i], v[9 + i]);
+    butterfly<16>(v, lane);
+    if ((lane & 1) == 0) {
+      float* slot = part + ((warp * NQ) + 8 * g + ((lane >> 1) & 7)) * 2 + (lane >> 4);
+      *slot = FIRST ? v[0] : *slot + v[0];
+    }
+  }
+  {
+    float v[4];
+    row2(16, v[0], v[1], v[2], v[3]);
+    butterfly<4>(v, lane);
+    if ((lane & 7) == 0) {
+      float* slot = part + ((warp * NQ) + 16 + ((lane >> 3) & 1)) * 2 + (lane >> 4);
+      *slot = FIRST ? v[0] : *slot + v[0];
+    }
+  }
+}
+
+template <int CORR>
+__device__ __forceinline__ void ln_finalize_q(uint8_t* sm, int rq, bool use_shift) {
+  const int tid = threadIdx.x;
+  float* part = reinterpret_cast<float*>(sm + OFF_PART);          // [16 warps][18 rows][2]
+  float* stats = reinterpret_cast<float*>(sm + OFF_STATS);        // pair layout (rstd, -mean * rstd)
+  float* means = reinterpret_cast<float*>(sm + OFF_MEAN);
+  const int r0 = NQ * rq;
   group_bar(rq);
   const int j = tid & 127;
   if (j < NQ) {
@@ -850,31 +907,38 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
       }
       ++aphase;
       stamp();   // 1: input projection consumed
-      auto dump_hidden = [&](int l) {     // ls_debug_hidden (parity aid; off in production: one uniform test per layer)
+      // ls_debug_hidden (parity aid; off in production: one uniform test per layer).  with_emb: h already carries the
+      // next block's time embedding (LS_LN1_EARLY), which is not part of "the residual stream after block l"
+      auto dump_hidden = [&](int l, bool with_emb) {
         if (p.dbg_h != nullptr && p.dbg_layer == l && valid && k == 0) {
 #pragma unroll
           for (int m = 0; m < 4; ++m)
 #pragma unroll
             for (int j = 0; j < NQ; ++j) {
               const int n = r0 + j;
-              if (n < R) p.dbg_h[((size_t)b * R + n) * LS_D + c0 + 128 * m] = h[m * NQ + j];
+              if (n < R) p.dbg_h[((size_t)b * R + n) * LS_D + c0 + 128 * m] = h[m * NQ + j] - (with_emb ? emb_s[c0 + 128 * m] : 0.f);
             }
         }
       };
-      dump_hidden(-1);
+      dump_hidden(-1, false);
 
       for (int l = 0; l < p.n_layers; ++l) {
         const LsLayerW L = p.w.layer[l];
         if (!TokBias<S>::kInGemm && tid < S) btok_s[tid] = btok_s[S + tid] = L.b_tok[tid];
         // x = x + emb ; LN1 ; -> operand tile
+        if (!LS_LN1_EARLY || l == 0) {
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const f32x2 emb = bc2(emb_s[c0 + 128 * m]);
+          for (int m = 0; m < 4; ++m) {
+            const f32x2 emb = bc2(emb_s[c0 + 128 * m]);
 #pragma unroll
-          for (int j = 0; j < NQ; j += 2) upk2(add2(pk2(h[m * NQ + j], h[m * NQ + j + 1]), emb), h[m * NQ + j], h[m * NQ + j + 1]);
+            for (int j = 0; j < NQ; j += 2) upk2(add2(pk2(h[m * NQ + j], h[m * NQ + j + 1]), emb), h[m * NQ + j], h[m * NQ + j + 1]);
+          }
+          if (l == 0) ln_stats_q<0>(h, sm, rq, false);     // provisional means for the shift
+          ln_stats_q<0>(h, sm, rq, true);
+        } else {
+          // the previous block's channel-mix epilogue added emb and accumulated the partial sums M-tile by M-tile
+          ln_finalize_q<0>(sm, rq, true);
         }
-        if (l == 0) ln_stats_q<0>(h, sm, rq, false);     // provisional means for the shift
-        ln_stats_q<0>(h, sm, rq, true);
         stamp();   // LN1 stats done
         auto publish_a = [&](int m) {   // this warp's part of the token-mix operand of M-tile m is in tensor memory
           tc_fence_before_sync();
@@ -939,11 +1003,22 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
               silu_acc2(h[m * NQ + j], h[m * NQ + j + 1], fma2(pk2(r.x, r.y), v, fma2(pk2(r.z, r.w), bc2(Sc), bc2(tc))));
           });
           if (m < 2) drained(BAR_DRAIN0 + m);
+          if (LS_LN1_EARLY && l + 1 < p.n_layers) {
+            // this M-tile's channels are final: add the next block's emb and account them in its LayerNorm-1 statistics
+            // now, under the MMAs of the later M-tiles, instead of after the last one
+            const f32x2 emb = bc2(emb_s[c0 + 128 * m]);
+#pragma unroll
+            for (int j = 0; j < NQ; j += 2) upk2(add2(pk2(h[m * NQ + j], h[m * NQ + j + 1]), emb), h[m * NQ + j], h[m * NQ + j + 1]);
+            if (m == 0)
+              ln_partial_q<true>(h + m * NQ, sm, rq);
+            else
+              ln_partial_q<false>(h + m * NQ, sm, rq);
+          }
           if (m == 2) stamp();   // three of four M-tiles consumed
         }
         ++aphase;
         stamp();   // channel-mix epilogue done
-        dump_hidden(l);
+        dump_hidden(l, LS_LN1_EARLY && l + 1 < p.n_layers);
       }
 
       // ---- output head operand: plain hi/lo split of h -------------------------------------
