@@ -82,7 +82,10 @@ constexpr int NSLOT = 4;
 #ifndef LS_LN1_EARLY
 // 1: the channel-mix epilogue of block l adds block l+1's time embedding and accumulates its LayerNorm-1 partial sums
 //    M-tile by M-tile (ln_partial_q), so that only the last butterfly and the 4-warp combine follow the last MMA.
-#define LS_LN1_EARLY 1
+//    Measured (profiles/r2_ab_power_cap.txt): the best launch gets 0.5 % shorter, but the kernel sits at the 1000 W power
+//    cap and the extra work (+ 15 % warp instructions, + 33 % LSU shared wavefronts: three more butterflies per block)
+//    comes back as a 0.8 % lower clock - net + 0.1 %; + 1.0 % only in the uncapped multicast build.  0 (default): off.
+#define LS_LN1_EARLY 0
 #endif
 #ifndef LS_NOFETCH
 #define LS_NOFETCH 0     // diagnostic: 1 = the producer signals stages without copying (garbage results, pure MMA timing)
