@@ -238,10 +238,11 @@ typedef struct ls_sag_weights {
 int ls_sag_decode(const ls_sag_weights* w, int32_t B, const float* x, const float* z,
                   const uint8_t* mask, float* out, void* stream);
 /* The same decoder on the tensor cores (tcgen05, bf16x3 split operands, fp32 accumulation; self-attention, softmax,
- * LayerNorm and GELU in fp32): ls_sag_create builds the weight tapes from *w (the pointed-to weights must stay valid
- * only during the call; biases / LayerNorm vectors / mapping / finallayer / pe / cross-attention matrices are read by
- * every decode and must stay valid for the handle's life) and the workspaces for max_batch clips (557 KB per clip);
- * ls_sag_decode_tc has ls_sag_decode's contract.  ls_sag_decode stays the exact-order fp32 cross-check.              */
+ * LayerNorm and GELU in fp32): ls_sag_create builds the weight tapes of the four projections per layer from *w and
+ * folds each layer's single-token cross-attention into one matrix (those matrices are read during the call only);
+ * biases / LayerNorm vectors / mapping / finallayer / pe are read by every decode and must stay valid for the handle's
+ * life.  Workspaces for max_batch clips (557 KB per clip) live in the handle.  ls_sag_decode_tc has ls_sag_decode's
+ * contract; ls_sag_decode stays the exact-order fp32 cross-check.  ls_sag_launch_count: kernels launched so far.     */
 typedef struct ls_sag ls_sag;
 int ls_sag_create(ls_sag** out, const ls_sag_weights* w, int32_t max_batch, int32_t device, void* stream);
 int ls_sag_decode_tc(ls_sag* s, int32_t B, const float* x, const float* z, const uint8_t* mask,

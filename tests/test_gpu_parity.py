@@ -975,3 +975,36 @@ def test_training_losses_forward_vs_reference_fixture(name, spec, golden_train):
     torch.manual_seed(1)
     r2 = diffusion.training_losses(model, x_start, t, model_kwargs={"y": y}, noise=noise)
     assert torch.isfinite((r2[0] if isinstance(r2, tuple) else r2)["loss"])
+
+
+@pytest.mark.parametrize("njoints,nfeats", [(9, 3), (47, 6)])
+def test_sag_decoder_tc_ragged_batches_and_beat_geometry(njoints, nfeats):
+    """Tensor-core SAG decode at batch sizes that leave partly filled 128-row tiles (B*34 rows: 1, 3, 5 and 131 clips)
+    and at the BEAT pose width (282 outputs: the final layer loops over blocks of 32), against the exact-order fp32
+    kernel; padded frames stay exactly zero."""
+    sd = synthetic.synth_sag_state_dict(seed=3) if (njoints, nfeats) == (9, 3) else None
+    dec = ls.Decoder_TRANSFORMER(njoints=njoints, nfeats=nfeats, latent_dim=512, n_pre_poses=4, use_style=False)
+    if sd is not None:
+        dec.load_state_dict(sd, strict=True)
+    else:
+        g0 = torch.Generator().manual_seed(5)
+        with torch.no_grad():
+            for p_ in dec.parameters():
+                p_.copy_(torch.randn(p_.shape, generator=g0) * (0.05 if p_.dim() > 1 else 0.1))
+            for lay in dec.seqTransDecoder.layers:
+                for n_ in (lay.norm1, lay.norm2, lay.norm3):
+                    n_.weight.add_(1.0)
+    dec = dec.to(DEV).eval()
+    g = torch.Generator().manual_seed(12)
+    for B in (1, 3, 5, 131):
+        x = 0.3 * torch.randn(B, njoints, nfeats, 34, generator=g).to(DEV)
+        z = torch.randn(B, 512, generator=g).to(DEV)
+        mask = torch.ones(B, 34, dtype=torch.bool, device=DEV)
+        mask[B // 2, 29:] = False
+        dec.impl = "tc"
+        a = dec({"x": x, "z": z, "mask": mask})["output"]
+        dec.impl = "simt"
+        b = dec({"x": x, "z": z, "mask": mask})["output"]
+        assert a.shape == (B, njoints, nfeats, 34) and torch.isfinite(a).all()
+        _close(a, b)
+        assert float(a[B // 2, :, :, 29:].abs().max()) == 0.0
