@@ -110,7 +110,11 @@ class ClockSampler:
                     try:
                         sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                         r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                        self.rows.append((time.perf_counter(), float(sm), float(mx), [n for n, b in bits if r & b]))
+                        try:        # board power and its limit (mW): direct evidence of a power-capped kernel
+                            pw = (pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, pynvml.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0)
+                        except Exception:
+                            pw = None
+                        self.rows.append((time.perf_counter(), float(sm), float(mx), [n for n, b in bits if r & b], pw))
                     except Exception:
                         pass
                     time.sleep(0.05)
@@ -163,8 +167,13 @@ class ClockSampler:
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         reasons = sorted({n for r in rows for n in r[3]})
-        return {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
-                "reasons": reasons, "samples": len(rows), "window": window, "via": self.how}
+        out = {"sm_mhz": statistics.median(r[1] for r in rows), "sm_max_mhz": max(r[2] for r in rows),
+               "reasons": reasons, "samples": len(rows), "window": window, "via": self.how}
+        pw = [r[4] for r in rows if len(r) > 4 and r[4] is not None]
+        if pw:
+            out["power_w"] = round(statistics.median(p[0] for p in pw), 1)
+            out["power_limit_w"] = round(max(p[1] for p in pw), 1)
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
