@@ -172,6 +172,7 @@ class ClockSampler:
         pw = [r[4] for r in rows if len(r) > 4 and r[4] is not None]
         if pw:
             out["power_w"] = round(statistics.median(p[0] for p in pw), 1)
+            out["power_w_max"] = round(max(p[0] for p in pw), 1)
             out["power_limit_w"] = round(max(p[1] for p in pw), 1)
         return out
 
