@@ -1008,3 +1008,46 @@ def test_sag_decoder_tc_ragged_batches_and_beat_geometry(njoints, nfeats):
         assert a.shape == (B, njoints, nfeats, 34) and torch.isfinite(a).all()
         _close(a, b)
         assert float(a[B // 2, :, :, 29:].abs().max()) == 0.0
+
+
+def test_error_paths_of_the_round2_entry_points():
+    """ls_cfg_backward without / with a mismatching saved forward, ls_sag_create / ls_sag_decode_tc / ls_huber_terms
+    argument checks: negative codes + messages, never a crash."""
+    import ctypes
+    from ctypes import c_void_p
+    from livelyspeaker_b200 import _cabi, sag
+    from livelyspeaker_b200._cabi import LsError
+    dims, sd, cfg, diffusion = build("ted", "ddim100")
+    eng = cfg.model.engine(2)
+    y = synthetic.synth_cond(dims, 2, device=DEV)
+    eng.set_cond(y, force=True)
+    g = torch.zeros(2, 9, 3, 34, device=DEV)
+    with pytest.raises(LsError):          # no saved forward yet
+        eng.cfg_backward(g, y["scale"])
+    z = torch.zeros(2, 1, 512, device=DEV)
+    eng.cfg_forward_grad(g, torch.zeros(2, dtype=torch.long, device=DEV), z, z, y["scale"])
+    assert torch.isfinite(eng.cfg_backward(g, y["scale"])).all()
+    eng3 = cfg.model.engine(3)
+    y3 = synthetic.synth_cond(dims, 3, device=DEV)
+    eng3.set_cond(y3, force=True)
+    with pytest.raises(LsError):          # the saved forward has another batch size
+        eng3.cfg_backward(torch.zeros(3, 9, 3, 34, device=DEV), y3["scale"])
+    lib = _cabi.load_library()
+    lib.ls_sag_create.argtypes = [ctypes.POINTER(c_void_p), ctypes.POINTER(sag.LsSagWeights), ctypes.c_int32, ctypes.c_int32,
+                                  c_void_p]
+    h = c_void_p()
+    W = sag.LsSagWeights()               # all zero: wrong geometry
+    assert lib.ls_sag_create(ctypes.byref(h), ctypes.byref(W), 4, 0, None) < 0 and not h.value
+    assert b"built for" in lib.ls_last_error(None)
+    dec = ls.Decoder_TRANSFORMER(latent_dim=512, n_pre_poses=4, use_style=False)
+    dec.load_state_dict(synthetic.synth_sag_state_dict(seed=3), strict=True)
+    dec = dec.to(DEV).eval()
+    dec({"x": torch.zeros(2, 9, 3, 34, device=DEV), "z": torch.zeros(2, 512, device=DEV),
+         "mask": torch.ones(2, 34, dtype=torch.bool, device=DEV)})
+    lib.ls_sag_decode_tc.argtypes = [c_void_p, ctypes.c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    buf = torch.zeros(3 * 27 * 34, device=DEV)
+    assert lib.ls_sag_decode_tc(dec._tc[2], 3, c_void_p(buf.data_ptr()), c_void_p(buf.data_ptr()), None,
+                                c_void_p(buf.data_ptr()), None) < 0           # batch 3 > max_batch 2 of this handle
+    with pytest.raises(LsError):          # a single frame has no frame differences
+        _cabi.huber_terms(torch.zeros(4, 1, device=DEV), torch.zeros(4, 1, device=DEV), None, None,
+                          torch.zeros(3, device=DEV))
