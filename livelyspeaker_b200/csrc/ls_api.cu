@@ -244,7 +244,7 @@ extern "C" int ls_finalize_weights(ls_handle* h, void* stream) {
   if (rc == 0) {      // tcgen05 path available: the WavEncoder's three wide convolutions run on the tensor cores too
     const float* wc[3] = {R("audio_encoder.feat_extractor.3.weight"), R("audio_encoder.feat_extractor.6.weight"),
                           R("audio_encoder.feat_extractor.9.weight")};
-    if ((rc = lsw_init(h, wc, s)) < 0) return rc;
+    if ((rc = lsw_init(h, wc, s, R("audio_encoder.feat_extractor.0.weight"))) < 0) return rc;
   }
   h->finalized = true;
   h->cond_batch = 0;

@@ -129,12 +129,14 @@ int lsk_cfg_update(ls_handle* h, int B, const ls_step_params* p, const float* ou
 int lsk_axpby(ls_handle* h, int64_t n, const float* a, const float* b, float ca, float cb, float* out,
               cudaStream_t s);
 // ls_wavenc_tc.cu
-int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s);
+int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s, const float* w0 = nullptr);   // w0: layer-1 weights
 void lsw_destroy(ls_handle* h);
 int lsw_available(const ls_handle* h);
 int lsw_conv(ls_handle* h, int layer, const float* in, const float* bias, float* out, int nb, int Li, int Lo,
              cudaStream_t s);
-int lsw_audio_proj(ls_handle* h, const float* af_cm, int nb, float* A, cudaStream_t s);   // A [nb*34][512] from af [nb][256][34]
+int lsw_audio_proj(ls_handle* h, const float* af_cm, int nb, float* A, cudaStream_t s);
+int lsw_encoder_fused(ls_handle* h, const float* audio, const float* w0, const float* b3, float* out_cm, int nb, int L0,
+                      int L1, int L2, int L3, int L4, cudaStream_t s);   // whole WavEncoder, InstanceNorm fused into the convs   // A [nb*34][512] from af [nb][256][34]
 // ls_fused.cu
 int lsf_init(ls_handle* h, cudaStream_t s);            // build bf16 weight tapes; 0 if available
 void lsf_destroy(ls_handle* h);

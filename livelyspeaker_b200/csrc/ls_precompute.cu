@@ -5,6 +5,8 @@
 //                                   scripts/model/RAG.py:106-120, 184-192
 //   time_embed(pe[t]) table         scripts/model/mlp_module.py:123-136
 // All fp32 on CUDA cores: this is < 2 % of a T=1000 loop.
+#include <cstdlib>
+
 #include "ls_internal.cuh"
 
 // ------------------------------------------------------------------------------------
@@ -132,9 +134,16 @@ int lsk_wav_encoder(ls_handle* h, int B, const float* audio, float* out_cm, cuda
   const float *w3 = W("audio_encoder.feat_extractor.9.weight"), *b3 = W("audio_encoder.feat_extractor.9.bias");
   // layers 2-4 on the tensor cores (bf16x3) unless the exact-order fp32 implementation is selected
   const bool tc = lsw_available(h) && ls_get_impl(h) != LS_IMPL_SIMT;
+  // LS_WAV_V1=1 (diagnostic): the round-1 pipeline (separate InstanceNorm passes) on the tensor-core path
+  static const bool v1 = getenv("LS_WAV_V1") != nullptr;
   for (int c0 = 0; c0 < B; c0 += h->wav_chunk) {
     const int nb = min(h->wav_chunk, B - c0);
     const float* a = audio + (size_t)c0 * L0;
+    if (tc && !v1) {
+      const int rc = lsw_encoder_fused(h, a, w0, b3, out_cm + (size_t)c0 * LS_AF * LS_F, nb, L0, L1, L2, L3, L4, s);
+      if (rc) return rc;
+      continue;
+    }
     conv1d_k15_kernel<5><<<dim3((L1 + CV_TL - 1) / CV_TL, 1, nb), 128, 0, s>>>(a, w0, b0, h->wav_a, 1, L0, 32, L1, 1600);
     LS_LAUNCH_CHECK(h);
     instnorm_lrelu_kernel<<<nb * 32, 256, 0, s>>>(h->wav_a, L1);

@@ -12,6 +12,9 @@
 // Layer 1 (1 input channel, 4 % of the flops) and InstanceNorm + LeakyReLU stay on the CUDA-core kernels.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+#include <cstring>
+
 #include "ls_internal.cuh"
 #include "ls_rows_gemm.cuh"
 #include "ls_tc.cuh"
@@ -154,6 +157,12 @@ struct WavTc {
   uint8_t* tape[3] = {nullptr, nullptr, nullptr};
   uint8_t* tape_a = nullptr;      // audio half of input_mapping (W_a [512 x 256]) for lsw_audio_proj
   bool attr_done = false;
+  // lsw_encoder_fused: per-tile partial sums and (mean, rstd) rows, grown on demand
+  void* v2_part = nullptr;
+  void* v2_stats = nullptr;
+  float w1_host[32 * 15] = {};     // layer-1 weights as a kernel parameter
+  size_t v2_part_elems = 0, v2_stats_elems = 0;
+  bool v2_attr_done = false;
 };
 
 template <int CO>
@@ -174,13 +183,15 @@ void lsw_destroy(ls_handle* h) {
     for (auto& t : w->tape)
       if (t) cudaFree(t);
     if (w->tape_a) cudaFree(w->tape_a);
+    if (w->v2_part) cudaFree(w->v2_part);
+    if (w->v2_stats) cudaFree(w->v2_stats);
     delete w;
     h->wavtc = nullptr;
   }
 }
 
 // w[i]: conv weights of layers 2..4 ([Co, Ci, 15]); builds the three tapes
-int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s) {
+int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s, const float* w0) {
   static const int CO[3] = {64, 128, 256}, CI[3] = {32, 64, 128};
   WavTc* wt = static_cast<WavTc*>(h->wavtc);
   if (!wt) {
@@ -209,6 +220,10 @@ int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s) {
   }
   lsrg::build_rows_tape_kernel<<<64, 256, 0, s>>>(h->w.w_a_t, LS_D, LS_AF, wt->tape_a);
   LS_LAUNCH_CHECK(h);
+  if (w0 != nullptr) {           // layer-1 weights [32][1][15] to the host once: they are passed as a kernel parameter
+    LS_CUDA(h, cudaMemcpyAsync(wt->w1_host, w0, sizeof(wt->w1_host), cudaMemcpyDeviceToHost, s));
+    LS_CUDA(h, cudaStreamSynchronize(s));
+  }
   for (int i = 0; i < 3; ++i) {
     build_conv_tape_kernel<<<64, 256, 0, s>>>(w[i], CO[i], CI[i], wt->tape[i]);
     LS_LAUNCH_CHECK(h);
@@ -238,4 +253,319 @@ int lsw_audio_proj(ls_handle* h, const float* af_cm, int nb, float* A, cudaStrea
       lsrg::AChanMajor34{af_cm, LS_AF}, wt->tape_a, rows, LS_AF, lsrg::EpiStore<false>{A, LS_D, nullptr});
   LS_LAUNCH_CHECK(h);
   return LS_OK;
+}
+
+// =====================================================================================================================
+// Round-2 WavEncoder pipeline: InstanceNorm fused away.
+//   audio_enc.py:9-19: Conv1d -> InstanceNorm1d -> LeakyReLU(0.3) three times, then a last Conv1d.  InstanceNorm needs the
+//   statistics of a whole (clip, channel) row, so the round-1 pipeline ran it as a separate pass over every layer's
+//   output (405 us of HBM traffic at B = 512).  Here
+//     * every conv writes its RAW accumulators (no bias: InstanceNorm removes a per-channel constant anyway) and, per
+//       128-position tile, the partial sums (sum a, sum a^2) of each output channel (deterministic: transposing warp
+//       butterflies + a fixed-order combine),
+//     * in_finalize_kernel turns the partials of a row into (mean, rstd) in fp64,
+//     * the NEXT conv applies (a - mean) * rstd and the LeakyReLU while it loads its input window.
+//   The tensor-core convs also load their input differently: the window of a 128-position tile is contiguous in memory
+//   (778 floats per input channel), so the CTA reads it coalesced into a shared fp32 staging row - normalising each
+//   element once - and the threads build their overlapping 16-tap im2col rows from shared memory.  The round-1 loader
+//   gathered 64 scalars per thread per chunk at a 24-byte stride (L1-wavefront-bound: 450 per warp per chunk).
+// =====================================================================================================================
+namespace {
+
+constexpr int C1 = 32, C1_TILE = 256, C1_STRIDE = 5, C1_PAD = 1600;
+
+// V values per lane in, lane idx holds the sum over the 32 lanes of value idx (V = 32: idx = lane)
+__device__ __forceinline__ void butterfly32(float* v, int lane) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const int xm = 16 >> s, half = 16 >> s;
+    const bool up = (lane & xm) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? v[j] : v[j + half];
+      const float keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, xm);
+    }
+  }
+}
+
+// layer 1: audio [B][L0] -> raw accumulators [B][32][L1] + partials part[b][c][tile] = (sum, sum of squares).
+// The 480 weights travel as a kernel PARAMETER (constant bank): every FMA takes its weight as a constant operand.  With
+// the weights in shared memory the kernel issued one LDS per FMA and was LSU-bound at 266 us for 517 MB of output.
+struct Conv1W { float w[C1 * CONV_K]; };
+__global__ void __launch_bounds__(C1_TILE) wav_conv1_kernel(const float* __restrict__ audio, const __grid_constant__ Conv1W cw,
+                                                            float* __restrict__ out, float2* __restrict__ part, int L0, int L1,
+                                                            int n_tiles) {
+  constexpr int XW = (C1_TILE - 1) * C1_STRIDE + CONV_K;
+  __shared__ float xs[XW + 1];
+  __shared__ float wpart[C1_TILE / 32][2 * C1];
+  const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lo0 = tile * C1_TILE, lo = lo0 + tid;
+  const float* ab = audio + (size_t)b * L0;
+  const int x0 = lo0 * C1_STRIDE - C1_PAD;
+  for (int i = tid; i < XW; i += C1_TILE) {
+    const int g = x0 + i;
+    xs[i] = (g >= 0 && g < L0) ? ab[g] : 0.f;
+  }
+  __syncthreads();
+  float x[CONV_K];
+#pragma unroll
+  for (int k = 0; k < CONV_K; ++k) x[k] = xs[tid * C1_STRIDE + k];
+  const bool valid = lo < L1;
+  float acc[C1];
+#pragma unroll
+  for (int c = 0; c < C1; ++c) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < CONV_K; ++k) a = fmaf(cw.w[c * CONV_K + k], x[k], a);
+    acc[c] = valid ? a : 0.f;
+    if (valid) out[((size_t)b * C1 + c) * L1 + lo] = a;
+  }
+  float sq[C1];
+#pragma unroll
+  for (int c = 0; c < C1; ++c) sq[c] = acc[c] * acc[c];
+  butterfly32(acc, lane);
+  butterfly32(sq, lane);
+  wpart[warp][lane] = acc[0];
+  wpart[warp][C1 + lane] = sq[0];
+  __syncthreads();
+  if (tid < 2 * C1) {
+    float t = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < C1_TILE / 32; ++wq) t += wpart[wq][tid];
+    float* dst = reinterpret_cast<float*>(part + ((size_t)b * C1 + (tid & (C1 - 1))) * n_tiles + tile);
+    dst[tid >> 5] = t;
+  }
+}
+
+// (mean, rstd) of every (clip, channel) row from its per-tile partial sums; fp64, fixed order
+__global__ void in_finalize_kernel(const float2* __restrict__ part, int n_rows, int n_tiles, int L, float2* __restrict__ stats) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  double s = 0.0, q = 0.0;
+  for (int t = 0; t < n_tiles; ++t) {
+    const float2 p = part[(size_t)r * n_tiles + t];
+    s += p.x;
+    q += p.y;
+  }
+  const double mean = s / L, var = fmax(q / L - mean * mean, 0.0);
+  stats[r] = make_float2((float)mean, (float)(1.0 / sqrt(var + 1e-5)));
+}
+
+template <int CO>
+struct Lay2 {
+  static constexpr uint32_t B_IMG = CO * 128;
+  static constexpr uint32_t STAGE = 2 * A_IMG + 2 * B_IMG;
+  static constexpr uint32_t RAW_ROW = 784;                             // floats per staged input channel (778 used)
+  static constexpr uint32_t OFF_RAW = 2 * STAGE;
+  static constexpr uint32_t OFF_WPART = OFF_RAW + CI_PER_CHUNK * RAW_ROW * 4;     // [4 warps][2 * CO] epilogue partials
+  static constexpr uint32_t OFF_BARS = OFF_WPART + 4 * 2 * CO * 4;
+  static constexpr uint32_t SMEM = OFF_BARS + 64 + 1024;
+};
+
+// layers 2-4.  in: RAW accumulators of the previous layer [B][Ci][Li] with in_stats [B][Ci] = (mean, rstd);
+// out: RAW accumulators [B][CO][Lo] and part[b][co][tile] (FINAL: out = accumulators + bias, no partials).
+template <int CO, bool FINAL>
+__global__ void __launch_bounds__(128, 1) wav_conv_tc2_kernel(const float* __restrict__ in, const float2* __restrict__ in_stats,
+                                                              const uint8_t* __restrict__ tape, const float* __restrict__ bias,
+                                                              float* __restrict__ out, float2* __restrict__ part, int Ci, int Li,
+                                                              int Lo, int n_tiles) {
+  using L = Lay2<CO>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* raw = reinterpret_cast<float*>(sm + L::OFF_RAW);
+  float* wpart = reinterpret_cast<float*>(sm + L::OFF_WPART);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::OFF_BARS);       // full[2], empty[2], acc
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L::OFF_BARS + 48);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, tile = blockIdx.x, lo0 = tile * 128, lo = lo0 + tid;
+  const bool valid = lo < Lo;
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<CO>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sm_s = smem_u32(sm), bars_s = smem_u32(bars);
+  const int n_chunks = Ci / CI_PER_CHUNK;
+  const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 128u;
+  constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
+  constexpr uint32_t idesc = idesc_bf16(128, CO, 0, 0);
+  // the tile's input window: 127 * 6 + 16 samples per channel from w0, clipped at the end of the row
+  constexpr int WIN = 127 * STRIDE + 16;
+  const int w0 = lo0 * STRIDE, n_ok = min(WIN, Li - w0);
+  const float* inb = in + (size_t)b * Ci * Li + w0;
+  const float2* stb = in_stats + (size_t)b * Ci;
+  constexpr int PER_T = (WIN + 127) / 128;          // 7 samples per thread per channel
+  float nx[CI_PER_CHUNK][PER_T];
+  auto load_raw = [&](int c) {                      // coalesced: consecutive threads, consecutive samples
+#pragma unroll
+    for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
+      const float* src = inb + (size_t)(c * CI_PER_CHUNK + cil) * Li;
+#pragma unroll
+      for (int i = 0; i < PER_T; ++i) {
+        const int idx = tid + 128 * i;
+        nx[cil][i] = idx < n_ok ? __ldg(src + idx) : 0.f;
+      }
+    }
+  };
+  load_raw(0);
+  for (int c = 0; c < n_chunks; ++c) {
+    const int s = c & 1;
+    uint8_t* stage = sm + s * L::STAGE;
+    // normalise (InstanceNorm of the previous layer) + LeakyReLU once per element, into the staging rows
+#pragma unroll
+    for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
+      const float2 st = __ldg(stb + c * CI_PER_CHUNK + cil);
+#pragma unroll
+      for (int i = 0; i < PER_T; ++i) {
+        const int idx = tid + 128 * i;
+        if (idx < (int)L::RAW_ROW) {
+          float v = (nx[cil][i] - st.x) * st.y;
+          v = v > 0.f ? v : 0.3f * v;
+          raw[cil * L::RAW_ROW + idx] = idx < n_ok ? v : 0.f;      // finite padding: tap 15 meets a zero weight
+        }
+      }
+    }
+    if (c + 1 < n_chunks) load_raw(c + 1);            // in flight during the im2col build and the MMAs
+    if (c >= 2) {                                     // the MMAs that read this stage (chunk c-2) are done
+      mbar_wait(&bars[2 + s], ((c >> 1) - 1) & 1);
+      tc_fence_after_sync();
+    }
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bars[s], 2 * L::B_IMG);
+      bulk_g2s(stage + 2 * A_IMG, tape + (size_t)c * 2 * L::B_IMG, 2 * L::B_IMG, &bars[s]);
+    }
+    __syncthreads();                                  // staging rows complete
+#pragma unroll
+    for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
+      const float2* wr = reinterpret_cast<const float2*>(raw + cil * L::RAW_ROW + tid * STRIDE);
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 t = valid ? wr[i] : make_float2(0.f, 0.f);
+        v[2 * i] = t.x;
+        v[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint4 hi, lw;
+        hi.x = pack_hi_lo(v[8 * hh + 0], v[8 * hh + 1], &lw.x);
+        hi.y = pack_hi_lo(v[8 * hh + 2], v[8 * hh + 3], &lw.y);
+        hi.z = pack_hi_lo(v[8 * hh + 4], v[8 * hh + 5], &lw.z);
+        hi.w = pack_hi_lo(v[8 * hh + 6], v[8 * hh + 7], &lw.w);
+        const uint32_t off = row_off + ((uint32_t)((cil * 2 + hh) ^ (tid & 7)) << 4);
+        *reinterpret_cast<uint4*>(stage + off) = hi;
+        *reinterpret_cast<uint4*>(stage + A_IMG + off) = lw;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();                                  // im2col stage complete; the staging rows may be overwritten
+    if (warp == 0) {
+      mbar_wait_s(bars_s + 8 * s, (c >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t a_hi = desc_lo32(sm_s + s * L::STAGE, 16), a_lo = desc_lo32(sm_s + s * L::STAGE + A_IMG, 16);
+      const uint32_t b_hi = desc_lo32(sm_s + s * L::STAGE + 2 * A_IMG, 16),
+                     b_lo = desc_lo32(sm_s + s * L::STAGE + 2 * A_IMG + L::B_IMG, 16);
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+#pragma unroll
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        umma_bf16_split_elect(tm, a_hi + 2 * ks, DH, b_hi + 2 * ks, DH, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+        umma_bf16_split_elect(tm, a_lo + 2 * ks, DH, b_hi + 2 * ks, DH, idesc, 1u);
+        umma_bf16_split_elect(tm, a_hi + 2 * ks, DH, b_lo + 2 * ks, DH, idesc, 1u);
+      }
+      umma_commit_s_elect(bars_s + 8 * (2 + s));
+      if (c == n_chunks - 1) umma_commit_s_elect(bars_s + 8 * 4);
+    }
+  }
+  mbar_wait(&bars[4], 0);
+  __syncwarp();
+  tc_fence_after_sync();
+  // epilogue: lane = output position, column = output channel
+  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
+  float* dst = out + (size_t)b * CO * Lo + lo;
+#pragma unroll 1
+  for (int c0 = 0; c0 < CO; c0 += 16) {
+    float v[32];
+    tmem_ld16(taddr + c0, v);
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) dst[(size_t)(c0 + j) * Lo] = FINAL ? v[j] + __ldg(bias + c0 + j) : v[j];
+    }
+    if (!FINAL) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = valid ? v[j] : 0.f;
+        v[16 + j] = v[j] * v[j];
+      }
+      butterfly32(v, lane);                           // lane = (square? << 4) | channel of this group
+      wpart[warp * 2 * CO + (lane >> 4) * CO + c0 + (lane & 15)] = v[0];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (!FINAL) {
+    for (int i = tid; i < 2 * CO; i += 128) {
+      const float t = (wpart[i] + wpart[2 * CO + i]) + (wpart[4 * CO + i] + wpart[6 * CO + i]);
+      float* d = reinterpret_cast<float*>(part + ((size_t)b * CO + (i % CO)) * n_tiles + tile);
+      d[i / CO] = t;
+    }
+  }
+  if (warp == 0) tmem_dealloc<CO>(tmem);
+}
+
+template <int CO, bool FINAL>
+int launch_conv2(ls_handle* h, const float* in, const float2* st, const uint8_t* tape, const float* bias, float* out,
+                 float2* part, int nb, int Ci, int Li, int Lo, cudaStream_t s) {
+  const int n_tiles = (Lo + 127) / 128;
+  wav_conv_tc2_kernel<CO, FINAL><<<dim3(n_tiles, nb), 128, Lay2<CO>::SMEM, s>>>(in, st, tape, bias, out, part, Ci, Li, Lo, n_tiles);
+  LS_LAUNCH_CHECK(h);
+  return LS_OK;
+}
+
+}  // namespace
+
+// The whole encoder with the InstanceNorm passes fused away (tensor-core path).  audio [nb][L0] -> out_cm [nb][256][34];
+// wav_a / wav_b: the handle's ping-pong buffers; w0: layer-1 weights [32][1][15]; b3: the last layer's bias.
+int lsw_encoder_fused(ls_handle* h, const float* audio, const float* /*w0: uploaded by lsw_init*/, const float* b3, float* out_cm,
+                      int nb, int L0, int L1, int L2, int L3, int L4, cudaStream_t s) {
+  WavTc* wt = static_cast<WavTc*>(h->wavtc);
+  if (!wt) return ls_fail(h, LS_EUNSUPPORTED, "tensor-core WavEncoder not initialised");
+  const int t1 = (L1 + C1_TILE - 1) / C1_TILE, t2 = (L2 + 127) / 128, t3 = (L3 + 127) / 128;
+  const size_t need_part = (size_t)nb * std::max(std::max(32 * t1, 64 * t2), 128 * t3), need_stats = (size_t)nb * 128;
+  if (wt->v2_part_elems < need_part || wt->v2_stats_elems < need_stats) {
+    if (wt->v2_part) cudaFree(wt->v2_part);
+    if (wt->v2_stats) cudaFree(wt->v2_stats);
+    wt->v2_part = nullptr; wt->v2_stats = nullptr; wt->v2_part_elems = wt->v2_stats_elems = 0;
+    if (cudaMalloc(&wt->v2_part, need_part * sizeof(float2)) != cudaSuccess ||
+        cudaMalloc(&wt->v2_stats, need_stats * sizeof(float2)) != cudaSuccess)
+      return ls_fail(h, LS_ENOMEM, "WavEncoder statistics buffers");
+    wt->v2_part_elems = need_part;
+    wt->v2_stats_elems = need_stats;
+  }
+  if (!wt->v2_attr_done) {
+    LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc2_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay2<64>::SMEM));
+    LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay2<128>::SMEM));
+    LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay2<256>::SMEM));
+    wt->v2_attr_done = true;
+  }
+  float2* part = static_cast<float2*>(wt->v2_part);
+  float2* stats = static_cast<float2*>(wt->v2_stats);
+  int rc;
+  Conv1W cw;
+  memcpy(cw.w, wt->w1_host, sizeof(cw.w));
+  wav_conv1_kernel<<<dim3(t1, nb), C1_TILE, 0, s>>>(audio, cw, h->wav_a, part, L0, L1, t1);
+  LS_LAUNCH_CHECK(h);
+  in_finalize_kernel<<<(nb * 32 + 255) / 256, 256, 0, s>>>(part, nb * 32, t1, L1, stats);
+  LS_LAUNCH_CHECK(h);
+  if ((rc = launch_conv2<64, false>(h, h->wav_a, stats, wt->tape[0], nullptr, h->wav_b, part, nb, 32, L1, L2, s))) return rc;
+  in_finalize_kernel<<<(nb * 64 + 255) / 256, 256, 0, s>>>(part, nb * 64, t2, L2, stats);
+  LS_LAUNCH_CHECK(h);
+  if ((rc = launch_conv2<128, false>(h, h->wav_b, stats, wt->tape[1], nullptr, h->wav_a, part, nb, 64, L2, L3, s))) return rc;
+  in_finalize_kernel<<<(nb * 128 + 255) / 256, 256, 0, s>>>(part, nb * 128, t3, L3, stats);
+  LS_LAUNCH_CHECK(h);
+  return launch_conv2<256, true>(h, h->wav_a, stats, wt->tape[2], b3, out_cm, nullptr, nb, 128, L3, L4, s);
 }
