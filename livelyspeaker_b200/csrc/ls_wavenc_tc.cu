@@ -365,8 +365,20 @@ struct Lay2 {
 
 // layers 2-4.  in: RAW accumulators of the previous layer [B][Ci][Li] with in_stats [B][Ci] = (mean, rstd);
 // out: RAW accumulators [B][CO][Lo] and part[b][co][tile] (FINAL: out = accumulators + bias, no partials).
+__device__ __forceinline__ void builders_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// 320 threads = 8 builder warps + a weight-producer warp + an MMA-issuer warp.
+//   builders (thread = position tid & 127, half tid >> 7): stage the tile's input window (normalised), cut their
+//     position's 16-tap im2col rows for two of the chunk's four channels, arrive on a_full[stage]; later the epilogue
+//     (warp w drains TMEM lanes 32 (w & 3) and its half of the channels);
+//   producer: requests a weight tile the moment the MMAs of its stage's previous user complete;
+//   MMA issuer: waits for a_full + the weight tile, issues the 12 MMAs of a chunk, commits the stage free.
+// Measured with clock64 stamps before this split (one 128-thread group doing everything, MMAs issued by warp 0 after a
+// block barrier): a chunk took norm 700 + build 450-870 + barriers 300 + "issue 12 MMAs" 600-1500 cycles - tcgen05.mma
+// issue blocks while the tensor pipe's queue is full, so the issuing warp sat there for the MMAs' own duration with the
+// other warps parked at the next barrier: build and MMA were serialised, and no loader change could move the kernel.
 template <int CO, bool FINAL>
-__global__ void __launch_bounds__(128, 1) wav_conv_tc2_kernel(const float* __restrict__ in, const float2* __restrict__ in_stats,
+__global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __restrict__ in, const float2* __restrict__ in_stats,
                                                               const uint8_t* __restrict__ tape, const float* __restrict__ bias,
                                                               float* __restrict__ out, float2* __restrict__ part, int Ci, int Li,
                                                               int Lo, int n_tiles) {
@@ -375,13 +387,17 @@ __global__ void __launch_bounds__(128, 1) wav_conv_tc2_kernel(const float* __res
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* raw = reinterpret_cast<float*>(sm + L::OFF_RAW);
   float* wpart = reinterpret_cast<float*>(sm + L::OFF_WPART);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::OFF_BARS);       // full[2], empty[2], acc
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L::OFF_BARS + 48);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::OFF_BARS);       // w_full[2], empty[2], acc, a_full[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L::OFF_BARS + 56);
+  enum { W_FULL0 = 0, EMPTY0 = 2, ACC = 4, A_FULL0 = 5 };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y, tile = blockIdx.x, lo0 = tile * 128, lo = lo0 + tid;
+  const int pos = tid & 127, half = (tid >> 7) & 1;
+  const int b = blockIdx.y, tile = blockIdx.x, lo0 = tile * 128, lo = lo0 + pos;
   const bool valid = lo < Lo;
   if (tid == 0) {
     for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bars[A_FULL0], 8);                     // one arrival per builder warp
+    mbar_init(&bars[A_FULL0 + 1], 8);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<CO>(tmem_slot);
@@ -391,124 +407,142 @@ __global__ void __launch_bounds__(128, 1) wav_conv_tc2_kernel(const float* __res
   const uint32_t tmem = *tmem_slot;
   const uint32_t sm_s = smem_u32(sm), bars_s = smem_u32(bars);
   const int n_chunks = Ci / CI_PER_CHUNK;
-  const uint32_t row_off = (uint32_t)(tid >> 3) * 1024u + (uint32_t)(tid & 7) * 128u;
-  constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
-  constexpr uint32_t idesc = idesc_bf16(128, CO, 0, 0);
-  // the tile's input window: 127 * 6 + 16 samples per channel from w0, clipped at the end of the row
-  constexpr int WIN = 127 * STRIDE + 16;
-  const int w0 = lo0 * STRIDE, n_ok = min(WIN, Li - w0);
-  const float* inb = in + (size_t)b * Ci * Li + w0;
-  const float2* stb = in_stats + (size_t)b * Ci;
-  constexpr int PER_T = (WIN + 127) / 128;          // 7 samples per thread per channel
-  float nx[CI_PER_CHUNK][PER_T];
-  auto load_raw = [&](int c) {                      // coalesced: consecutive threads, consecutive samples
-#pragma unroll
-    for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
-      const float* src = inb + (size_t)(c * CI_PER_CHUNK + cil) * Li;
-#pragma unroll
-      for (int i = 0; i < PER_T; ++i) {
-        const int idx = tid + 128 * i;
-        nx[cil][i] = idx < n_ok ? __ldg(src + idx) : 0.f;
+
+  if (warp == 8) {
+    // ================= weight producer ==============================================================
+    if (lane == 0) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c & 1;
+        if (c >= 2) mbar_wait(&bars[EMPTY0 + s], ((c >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[W_FULL0 + s], 2 * L::B_IMG);
+        bulk_g2s(sm + s * L::STAGE + 2 * A_IMG, tape + (size_t)c * 2 * L::B_IMG, 2 * L::B_IMG, &bars[W_FULL0 + s]);
       }
     }
-  };
-  load_raw(0);
-  for (int c = 0; c < n_chunks; ++c) {
-    const int s = c & 1;
-    uint8_t* stage = sm + s * L::STAGE;
-    // normalise (InstanceNorm of the previous layer) + LeakyReLU once per element, into the staging rows
-#pragma unroll
-    for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
-      const float2 st = __ldg(stb + c * CI_PER_CHUNK + cil);
-#pragma unroll
-      for (int i = 0; i < PER_T; ++i) {
-        const int idx = tid + 128 * i;
-        if (idx < (int)L::RAW_ROW) {
-          float v = (nx[cil][i] - st.x) * st.y;
-          v = v > 0.f ? v : 0.3f * v;
-          raw[cil * L::RAW_ROW + idx] = idx < n_ok ? v : 0.f;      // finite padding: tap 15 meets a zero weight
-        }
-      }
-    }
-    if (c + 1 < n_chunks) load_raw(c + 1);            // in flight during the im2col build and the MMAs
-    if (c >= 2) {                                     // the MMAs that read this stage (chunk c-2) are done
-      mbar_wait(&bars[2 + s], ((c >> 1) - 1) & 1);
-      tc_fence_after_sync();
-    }
-    if (tid == 0) {
-      mbar_arrive_expect_tx(&bars[s], 2 * L::B_IMG);
-      bulk_g2s(stage + 2 * A_IMG, tape + (size_t)c * 2 * L::B_IMG, 2 * L::B_IMG, &bars[s]);
-    }
-    __syncthreads();                                  // staging rows complete
-#pragma unroll
-    for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
-      const float2* wr = reinterpret_cast<const float2*>(raw + cil * L::RAW_ROW + tid * STRIDE);
-      float v[16];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float2 t = valid ? wr[i] : make_float2(0.f, 0.f);
-        v[2 * i] = t.x;
-        v[2 * i + 1] = t.y;
-      }
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        uint4 hi, lw;
-        hi.x = pack_hi_lo(v[8 * hh + 0], v[8 * hh + 1], &lw.x);
-        hi.y = pack_hi_lo(v[8 * hh + 2], v[8 * hh + 3], &lw.y);
-        hi.z = pack_hi_lo(v[8 * hh + 4], v[8 * hh + 5], &lw.z);
-        hi.w = pack_hi_lo(v[8 * hh + 6], v[8 * hh + 7], &lw.w);
-        const uint32_t off = row_off + ((uint32_t)((cil * 2 + hh) ^ (tid & 7)) << 4);
-        *reinterpret_cast<uint4*>(stage + off) = hi;
-        *reinterpret_cast<uint4*>(stage + A_IMG + off) = lw;
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();                                  // im2col stage complete; the staging rows may be overwritten
-    if (warp == 0) {
-      mbar_wait_s(bars_s + 8 * s, (c >> 1) & 1);
+  } else if (warp == 9) {
+    // ================= MMA issuer: whole warp in uniform control flow, one elected lane issues ========
+    constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
+    constexpr uint32_t idesc = idesc_bf16(128, CO, 0, 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c & 1;
+      mbar_wait_s(bars_s + 8 * (A_FULL0 + s), (c >> 1) & 1);
+      mbar_wait_s(bars_s + 8 * (W_FULL0 + s), (c >> 1) & 1);
       tc_fence_after_sync();
       const uint32_t a_hi = desc_lo32(sm_s + s * L::STAGE, 16), a_lo = desc_lo32(sm_s + s * L::STAGE + A_IMG, 16);
       const uint32_t b_hi = desc_lo32(sm_s + s * L::STAGE + 2 * A_IMG, 16),
                      b_lo = desc_lo32(sm_s + s * L::STAGE + 2 * A_IMG + L::B_IMG, 16);
-      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
 #pragma unroll
       for (uint32_t ks = 0; ks < 4; ++ks) {
         umma_bf16_split_elect(tm, a_hi + 2 * ks, DH, b_hi + 2 * ks, DH, idesc, (c > 0 || ks > 0) ? 1u : 0u);
         umma_bf16_split_elect(tm, a_lo + 2 * ks, DH, b_hi + 2 * ks, DH, idesc, 1u);
         umma_bf16_split_elect(tm, a_hi + 2 * ks, DH, b_lo + 2 * ks, DH, idesc, 1u);
       }
-      umma_commit_s_elect(bars_s + 8 * (2 + s));
-      if (c == n_chunks - 1) umma_commit_s_elect(bars_s + 8 * 4);
+      umma_commit_s_elect(bars_s + 8 * (EMPTY0 + s));
     }
-  }
-  mbar_wait(&bars[4], 0);
-  __syncwarp();
-  tc_fence_after_sync();
-  // epilogue: lane = output position, column = output channel
-  const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-  float* dst = out + (size_t)b * CO * Lo + lo;
-#pragma unroll 1
-  for (int c0 = 0; c0 < CO; c0 += 16) {
-    float v[32];
-    tmem_ld16(taddr + c0, v);
-    if (valid) {
+    umma_commit_s_elect(bars_s + 8 * ACC);
+  } else {
+    // ================= builders, then the epilogue ====================================================
+    const uint32_t row_off = (uint32_t)(pos >> 3) * 1024u + (uint32_t)(pos & 7) * 128u;
+    // the tile's input window: 127 * 6 + 16 samples per channel from w0, clipped at the end of the row
+    constexpr int WIN = 127 * STRIDE + 16;
+    const int w0 = lo0 * STRIDE, n_ok = min(WIN, Li - w0);
+    const float* inb = in + (size_t)b * Ci * Li + w0;
+    const float2* stb = in_stats + (size_t)b * Ci;
+    constexpr int PER_T = (WIN + 255) / 256;          // 4 samples per thread per channel
+    float nx[CI_PER_CHUNK][PER_T];
+    auto load_raw = [&](int c) {                      // coalesced: consecutive threads, consecutive samples
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dst[(size_t)(c0 + j) * Lo] = FINAL ? v[j] + __ldg(bias + c0 + j) : v[j];
-    }
-    if (!FINAL) {
+      for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
+        const float* src = inb + (size_t)(c * CI_PER_CHUNK + cil) * Li;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] = valid ? v[j] : 0.f;
-        v[16 + j] = v[j] * v[j];
+        for (int i = 0; i < PER_T; ++i) {
+          const int idx = tid + 256 * i;
+          nx[cil][i] = idx < n_ok ? __ldg(src + idx) : 0.f;
+        }
       }
-      butterfly32(v, lane);                           // lane = (square? << 4) | channel of this group
-      wpart[warp * 2 * CO + (lane >> 4) * CO + c0 + (lane & 15)] = v[0];
+    };
+    load_raw(0);
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c & 1;
+      uint8_t* stage = sm + s * L::STAGE;
+      // normalise (InstanceNorm of the previous layer) + LeakyReLU once per element, into the staging rows
+#pragma unroll
+      for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
+        const float2 st = __ldg(stb + c * CI_PER_CHUNK + cil);
+#pragma unroll
+        for (int i = 0; i < PER_T; ++i) {
+          const int idx = tid + 256 * i;
+          if (idx < (int)L::RAW_ROW) {
+            float v = (nx[cil][i] - st.x) * st.y;
+            v = v > 0.f ? v : 0.3f * v;
+            raw[cil * L::RAW_ROW + idx] = idx < n_ok ? v : 0.f;      // finite padding: tap 15 meets a zero weight
+          }
+        }
+      }
+      if (c + 1 < n_chunks) load_raw(c + 1);          // in flight during the im2col build
+      if (c >= 2) {                                   // the MMAs that read this stage (chunk c-2) are done
+        mbar_wait(&bars[EMPTY0 + s], ((c >> 1) - 1) & 1);
+      }
+      builders_bar();                                 // staging rows complete
+#pragma unroll
+      for (int cc = 0; cc < CI_PER_CHUNK / 2; ++cc) {
+        const int cil = 2 * half + cc;
+        const float2* wr = reinterpret_cast<const float2*>(raw + cil * L::RAW_ROW + pos * STRIDE);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 t = valid ? wr[i] : make_float2(0.f, 0.f);
+          v[2 * i] = t.x;
+          v[2 * i + 1] = t.y;
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint4 hi, lw;
+          hi.x = pack_hi_lo(v[8 * hh + 0], v[8 * hh + 1], &lw.x);
+          hi.y = pack_hi_lo(v[8 * hh + 2], v[8 * hh + 3], &lw.y);
+          hi.z = pack_hi_lo(v[8 * hh + 4], v[8 * hh + 5], &lw.z);
+          hi.w = pack_hi_lo(v[8 * hh + 6], v[8 * hh + 7], &lw.w);
+          const uint32_t off = row_off + ((uint32_t)((cil * 2 + hh) ^ (pos & 7)) << 4);
+          *reinterpret_cast<uint4*>(stage + off) = hi;
+          *reinterpret_cast<uint4*>(stage + A_IMG + off) = lw;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[A_FULL0 + s]);
+      builders_bar();                                 // every builder is done with the staging rows
     }
+    mbar_wait(&bars[ACC], 0);
+    __syncwarp();
+    tc_fence_after_sync();
+    // epilogue: lane = output position, column = output channel; the two halves split the channels
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* dst = out + (size_t)b * CO * Lo + lo;
+#pragma unroll 1
+    for (int c0 = half * (CO / 2); c0 < (half + 1) * (CO / 2); c0 += 16) {
+      float v[32];
+      tmem_ld16(taddr + c0, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[(size_t)(c0 + j) * Lo] = FINAL ? v[j] + __ldg(bias + c0 + j) : v[j];
+      }
+      if (!FINAL) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = valid ? v[j] : 0.f;
+          v[16 + j] = v[j] * v[j];
+        }
+        butterfly32(v, lane);                         // lane = (square? << 4) | channel of this group
+        wpart[(warp & 3) * 2 * CO + (lane >> 4) * CO + c0 + (lane & 15)] = v[0];
+      }
+    }
+    tc_fence_before_sync();
   }
-  tc_fence_before_sync();
   __syncthreads();
   if (!FINAL) {
-    for (int i = tid; i < 2 * CO; i += 128) {
+    for (int i = tid; i < 2 * CO; i += 320) {
       const float t = (wpart[i] + wpart[2 * CO + i]) + (wpart[4 * CO + i] + wpart[6 * CO + i]);
       float* d = reinterpret_cast<float*>(part + ((size_t)b * CO + (i % CO)) * n_tiles + tile);
       d[i / CO] = t;
@@ -521,7 +555,7 @@ template <int CO, bool FINAL>
 int launch_conv2(ls_handle* h, const float* in, const float2* st, const uint8_t* tape, const float* bias, float* out,
                  float2* part, int nb, int Ci, int Li, int Lo, cudaStream_t s) {
   const int n_tiles = (Lo + 127) / 128;
-  wav_conv_tc2_kernel<CO, FINAL><<<dim3(n_tiles, nb), 128, Lay2<CO>::SMEM, s>>>(in, st, tape, bias, out, part, Ci, Li, Lo, n_tiles);
+  wav_conv_tc2_kernel<CO, FINAL><<<dim3(n_tiles, nb), 320, Lay2<CO>::SMEM, s>>>(in, st, tape, bias, out, part, Ci, Li, Lo, n_tiles);
   LS_LAUNCH_CHECK(h);
   return LS_OK;
 }
