@@ -292,6 +292,8 @@ __device__ __forceinline__ void butterfly32(float* v, int lane) {
 // layer 1: audio [B][L0] -> raw accumulators [B][32][L1] + partials part[b][c][tile] = (sum, sum of squares).
 // The 480 weights travel as a kernel PARAMETER (constant bank): every FMA takes its weight as a constant operand.  With
 // the weights in shared memory the kernel issued one LDS per FMA and was LSU-bound at 266 us for 517 MB of output.
+// Now instruction-issue-bound (75 % issue-active, 223 us).  Tried: two positions per thread to pay the statistics'
+// butterflies once per thread - 148 registers halve the occupancy and the kernel gets slower (even at 128 registers).
 struct Conv1W { float w[C1 * CONV_K]; };
 __global__ void __launch_bounds__(C1_TILE) wav_conv1_kernel(const float* __restrict__ audio, const __grid_constant__ Conv1W cw,
                                                             float* __restrict__ out, float2* __restrict__ part, int L0, int L1,
@@ -551,6 +553,183 @@ __global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __res
   if (warp == 0) tmem_dealloc<CO>(tmem);
 }
 
+// The LAST layer (Conv1d(128, 256, 15, 6), 217 -> 34 positions, bias, no norm after it) with the rows of a tile taken from
+// SEVERAL clips: one clip has only 34 output positions, so a tile per clip left 73 % of every MMA's rows empty.  Tile row
+// r = global position g0 + r, clip g / 34, position g % 34; a tile spans at most 5 clips, whose whole input rows (217
+// samples per channel, padded to 218 floats so that every window start stays 8-byte aligned) are staged per chunk.
+constexpr int P_LO = 34, P_LI = 217, P_ROW = 218, P_CLIPS = 5, P_CO = 256;
+struct LayP {
+  static constexpr uint32_t B_IMG = P_CO * 128;
+  static constexpr uint32_t STAGE = 2 * A_IMG + 2 * B_IMG;
+  static constexpr uint32_t OFF_RAW = 2 * STAGE;
+  static constexpr uint32_t RAW_FLOATS = P_CLIPS * CI_PER_CHUNK * P_ROW;        // 4360
+  static constexpr uint32_t OFF_ST = OFF_RAW + RAW_FLOATS * 4;                    // [5 clips][4 channels] (mean, rstd)
+  static constexpr uint32_t OFF_BARS = OFF_ST + P_CLIPS * CI_PER_CHUNK * 8;
+  static constexpr uint32_t SMEM = OFF_BARS + 64 + 1024;
+};
+static_assert(LayP::SMEM <= 232448, "shared memory budget of the packed last layer");
+
+__global__ void __launch_bounds__(320, 1) wav_conv4_packed_kernel(const float* __restrict__ in, const float2* __restrict__ in_stats,
+                                                                  const uint8_t* __restrict__ tape, const float* __restrict__ bias,
+                                                                  float* __restrict__ out, int Ci, int n_rows) {
+  using L = LayP;
+  constexpr int CO = P_CO;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* raw = reinterpret_cast<float*>(sm + L::OFF_RAW);
+  float2* st_s = reinterpret_cast<float2*>(sm + L::OFF_ST);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L::OFF_BARS);       // w_full[2], empty[2], acc, a_full[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + L::OFF_BARS + 56);
+  enum { W_FULL0 = 0, EMPTY0 = 2, ACC = 4, A_FULL0 = 5 };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pos = tid & 127, half = (tid >> 7) & 1;
+  const int g0 = blockIdx.x * 128, g = g0 + pos;
+  const bool valid = g < n_rows;
+  const int clip0 = g0 / P_LO;
+  const int n_clips_total = n_rows / P_LO;
+  if (tid == 0) {
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&bars[A_FULL0], 8);
+    mbar_init(&bars[A_FULL0 + 1], 8);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<CO>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sm_s = smem_u32(sm), bars_s = smem_u32(bars);
+  const int n_chunks = Ci / CI_PER_CHUNK;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int c = 0; c < n_chunks; ++c) {
+        const int s = c & 1;
+        if (c >= 2) mbar_wait(&bars[EMPTY0 + s], ((c >> 1) - 1) & 1);
+        mbar_arrive_expect_tx(&bars[W_FULL0 + s], 2 * L::B_IMG);
+        bulk_g2s(sm + s * L::STAGE + 2 * A_IMG, tape + (size_t)c * 2 * L::B_IMG, 2 * L::B_IMG, &bars[W_FULL0 + s]);
+      }
+    }
+  } else if (warp == 9) {
+    constexpr uint32_t DH = desc_hi32(1024, (uint32_t)SWZ_128B);
+    constexpr uint32_t idesc = idesc_bf16(128, CO, 0, 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c & 1;
+      mbar_wait_s(bars_s + 8 * (A_FULL0 + s), (c >> 1) & 1);
+      mbar_wait_s(bars_s + 8 * (W_FULL0 + s), (c >> 1) & 1);
+      tc_fence_after_sync();
+      const uint32_t a_hi = desc_lo32(sm_s + s * L::STAGE, 16), a_lo = desc_lo32(sm_s + s * L::STAGE + A_IMG, 16);
+      const uint32_t b_hi = desc_lo32(sm_s + s * L::STAGE + 2 * A_IMG, 16),
+                     b_lo = desc_lo32(sm_s + s * L::STAGE + 2 * A_IMG + L::B_IMG, 16);
+#pragma unroll
+      for (uint32_t ks = 0; ks < 4; ++ks) {
+        umma_bf16_split_elect(tm, a_hi + 2 * ks, DH, b_hi + 2 * ks, DH, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+        umma_bf16_split_elect(tm, a_lo + 2 * ks, DH, b_hi + 2 * ks, DH, idesc, 1u);
+        umma_bf16_split_elect(tm, a_hi + 2 * ks, DH, b_lo + 2 * ks, DH, idesc, 1u);
+      }
+      umma_commit_s_elect(bars_s + 8 * (EMPTY0 + s));
+    }
+    umma_commit_s_elect(bars_s + 8 * ACC);
+  } else {
+    const uint32_t row_off = (uint32_t)(pos >> 3) * 1024u + (uint32_t)(pos & 7) * 128u;
+    // staged elements of this thread: e = tid + 256 i over [clip j][channel cil][sample k < 217]; chunk-invariant parts
+    constexpr int N_E = P_CLIPS * CI_PER_CHUNK * P_LI;          // 4340
+    constexpr int PER_T = (N_E + 255) / 256;                    // 17
+    int goff[PER_T];                 // global offset without the chunk's channel base, or -1
+    short soff[PER_T], sidx[PER_T];  // staging offset; (j * 4 + cil) for the statistics
+#pragma unroll
+    for (int i = 0; i < PER_T; ++i) {
+      const int e = tid + 256 * i;
+      const int jc = e / P_LI, k = e - jc * P_LI, j = jc >> 2, cil = jc & 3;
+      const bool ok = e < N_E && clip0 + j < n_clips_total;
+      goff[i] = ok ? ((clip0 + j) * Ci + cil) * P_LI + k : -1;
+      soff[i] = (short)(e < N_E ? jc * P_ROW + k : -1);
+      sidx[i] = (short)jc;
+    }
+    float nx[PER_T];
+    auto load_raw = [&](int c) {
+#pragma unroll
+      for (int i = 0; i < PER_T; ++i) nx[i] = goff[i] >= 0 ? __ldg(in + goff[i] + c * CI_PER_CHUNK * P_LI) : 0.f;
+    };
+    auto load_stats = [&](int c) {   // (mean, rstd) of the chunk's 4 channels for the tile's clips
+      if (tid < P_CLIPS * CI_PER_CHUNK) {
+        const int j = tid >> 2, cil = tid & 3;
+        st_s[tid] = clip0 + j < n_clips_total ? __ldg(in_stats + (size_t)(clip0 + j) * Ci + c * CI_PER_CHUNK + cil)
+                                              : make_float2(0.f, 1.f);
+      }
+    };
+    const int my_j = valid ? g / P_LO - clip0 : 0, my_lo = valid ? g % P_LO : 0;
+    load_raw(0);
+    load_stats(0);
+    builders_bar();
+#pragma unroll 1
+    for (int c = 0; c < n_chunks; ++c) {
+      const int s = c & 1;
+      uint8_t* stage = sm + s * L::STAGE;
+#pragma unroll
+      for (int i = 0; i < PER_T; ++i) {
+        if (soff[i] >= 0) {
+          const float2 st = st_s[sidx[i]];
+          float v = (nx[i] - st.x) * st.y;
+          v = v > 0.f ? v : 0.3f * v;
+          raw[soff[i]] = goff[i] >= 0 ? v : 0.f;
+        }
+      }
+      if (tid < P_CLIPS * CI_PER_CHUNK) raw[tid * P_ROW + P_LI] = 0.f;       // the pad sample (zero-weight 16th tap of the last window)
+      if (c + 1 < n_chunks) load_raw(c + 1);
+      if (c >= 2) mbar_wait(&bars[EMPTY0 + s], ((c >> 1) - 1) & 1);
+      builders_bar();                                 // staging rows complete; everybody has read this chunk's statistics
+      if (c + 1 < n_chunks) load_stats(c + 1);
+#pragma unroll
+      for (int cc = 0; cc < CI_PER_CHUNK / 2; ++cc) {
+        const int cil = 2 * half + cc;
+        const float2* wr = reinterpret_cast<const float2*>(raw + (my_j * CI_PER_CHUNK + cil) * P_ROW + my_lo * STRIDE);
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float2 t = valid ? wr[i] : make_float2(0.f, 0.f);
+          v[2 * i] = t.x;
+          v[2 * i + 1] = t.y;
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint4 hi, lw;
+          hi.x = pack_hi_lo(v[8 * hh + 0], v[8 * hh + 1], &lw.x);
+          hi.y = pack_hi_lo(v[8 * hh + 2], v[8 * hh + 3], &lw.y);
+          hi.z = pack_hi_lo(v[8 * hh + 4], v[8 * hh + 5], &lw.z);
+          hi.w = pack_hi_lo(v[8 * hh + 6], v[8 * hh + 7], &lw.w);
+          const uint32_t off = row_off + ((uint32_t)((cil * 2 + hh) ^ (pos & 7)) << 4);
+          *reinterpret_cast<uint4*>(stage + off) = hi;
+          *reinterpret_cast<uint4*>(stage + A_IMG + off) = lw;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[A_FULL0 + s]);
+      builders_bar();                                 // every builder is done with the staging rows (and st_s is rewritten)
+    }
+    mbar_wait(&bars[ACC], 0);
+    __syncwarp();
+    tc_fence_after_sync();
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* dst = out + ((size_t)(clip0 + my_j) * CO) * P_LO + my_lo;
+#pragma unroll 1
+    for (int c0 = half * (CO / 2); c0 < (half + 1) * (CO / 2); c0 += 16) {
+      float v[16];
+      tmem_ld16(taddr + c0, v);
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dst[(size_t)(c0 + j) * P_LO] = v[j] + __ldg(bias + c0 + j);
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<CO>(tmem);
+}
+
 template <int CO, bool FINAL>
 int launch_conv2(ls_handle* h, const float* in, const float2* st, const uint8_t* tape, const float* bias, float* out,
                  float2* part, int nb, int Ci, int Li, int Lo, cudaStream_t s) {
@@ -584,6 +763,7 @@ int lsw_encoder_fused(ls_handle* h, const float* audio, const float* /*w0: uploa
     LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc2_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay2<64>::SMEM));
     LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc2_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay2<128>::SMEM));
     LS_CUDA(h, cudaFuncSetAttribute(wav_conv_tc2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay2<256>::SMEM));
+    LS_CUDA(h, cudaFuncSetAttribute(wav_conv4_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LayP::SMEM));
     wt->v2_attr_done = true;
   }
   float2* part = static_cast<float2*>(wt->v2_part);
@@ -601,5 +781,10 @@ int lsw_encoder_fused(ls_handle* h, const float* audio, const float* /*w0: uploa
   if ((rc = launch_conv2<128, false>(h, h->wav_b, stats, wt->tape[1], nullptr, h->wav_a, part, nb, 64, L2, L3, s))) return rc;
   in_finalize_kernel<<<(nb * 128 + 255) / 256, 256, 0, s>>>(part, nb * 128, t3, L3, stats);
   LS_LAUNCH_CHECK(h);
+  if (L3 == P_LI && L4 == P_LO) {                     // the shipped geometry: tiles packed across clips
+    wav_conv4_packed_kernel<<<(nb * P_LO + 127) / 128, 320, LayP::SMEM, s>>>(h->wav_a, stats, wt->tape[2], b3, out_cm, 128, nb * P_LO);
+    LS_LAUNCH_CHECK(h);
+    return LS_OK;
+  }
   return launch_conv2<256, true>(h, h->wav_a, stats, wt->tape[2], b3, out_cm, nullptr, nb, 128, L3, L4, s);
 }
