@@ -64,14 +64,15 @@ def main():
         batch = {"x": y['origin_x'].clone(), 'mask': torch.ones(B, 34, device=device).bool(), 'z': z}
         init_image = sag(batch)['output']                             # decoded_motions
         skip_steps = 80 if a.ddim else 800
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        sample = sample_fn(model, (B, model.njoints, model.nfeats, 34), clip_denoised=False, model_kwargs=cond,
-                           skip_timesteps=skip_steps, init_image=init_image, progress=False, dump_steps=None, noise=None,
-                           const_noise=False)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    for attempt in range(2):       # the first call also builds the engine (weight upload, bf16 tapes, embedding table)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            sample = sample_fn(model, (B, model.njoints, model.nfeats, 34), clip_denoised=False, model_kwargs=cond,
+                               skip_timesteps=skip_steps, init_image=init_image, progress=False, dump_steps=None,
+                               noise=None, const_noise=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
     aligned_motions = sample.permute(0, 3, 1, 2).reshape(B, 34, -1)   # what the evaluators consume
     n = diffusion.num_timesteps - skip_steps
     print("%s: %d clips x %d steps in %.1f ms (%.0f clips/s), motions %s, finite=%s"
