@@ -6,7 +6,7 @@ attribute tables) for the SAMPLING path: schedules (:26-70), derived fp64 tables
 p_mean_variance (:284-399), p_sample (:507-558), p_sample_loop[_progressive]
 (:608-743), ddim_sample (:745-798), ddim_sample_loop[_progressive] (:895-1014),
 condition_mean / condition_score (:429-481), plms_sample[_loop] (:1016-1211),
-_extract_into_tensor (:1651-1664), and the *_with_grad samplers (:444-505, :560-606,
+_extract_into_tensor (:1651-1664), ddim_reverse_sample (:857-893), and the *_with_grad samplers (:444-505, :560-606,
 :800-855) whose model call is differentiable with respect to x through a hand-written
 backward kernel (ls_cfg_forward_grad / ls_cfg_backward).  Training losses and VLB terms
 need gradients with respect to the weights: outside the hot path,
@@ -818,5 +818,15 @@ class GaussianDiffusion:
             return terms
         return terms, {'target': target, 'model_output': model_output}
 
-    ddim_reverse_sample = _out_of_scope
+    def ddim_reverse_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, model_kwargs=None, eta=0.0):
+        """Sample x_{t+1} with the DDIM reverse ODE (gaussian_diffusion.py:857-893).  Generic route: the model call is
+        the fused kernel in mode 2 (ls_cfg_forward), two style draws per call like every other model call."""
+        assert eta == 0.0, "Reverse ODE only for deterministic path"
+        out = self.p_mean_variance(model, x, t, clip_denoised=clip_denoised, denoised_fn=denoised_fn,
+                                   model_kwargs=model_kwargs)
+        eps = ((_extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x.shape) * x - out["pred_xstart"])
+               / _extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x.shape))
+        alpha_bar_next = _extract_into_tensor(self.alphas_cumprod_next, t, x.shape)
+        mean_pred = out["pred_xstart"] * th.sqrt(alpha_bar_next) + th.sqrt(1 - alpha_bar_next) * eps
+        return {"sample": mean_pred, "pred_xstart": out["pred_xstart"]}
     calc_bpd_loop = _vb_terms_bpd = _prior_bpd = _out_of_scope

@@ -183,6 +183,15 @@ def ddim_sample_with_grad_step(sd, tab, tmap, x, i, y, tape, nj, nf, cond_fn, et
     return mean + nz * sigma * noise, x0_orig.detach()
 
 
+def ddim_reverse_step(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised=False):
+    """ddim_reverse_sample (gaussian_diffusion.py:857-893): x_i -> x_{i+1} along the deterministic DDIM ODE.  One model
+    call (two style draws), no step noise.  Returns (sample, pred_xstart)."""
+    x0 = _model_x0(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised)
+    eps = (_pick(tab["sqrt_recip_alphas_cumprod"], i) * x - x0) / _pick(tab["sqrt_recipm1_alphas_cumprod"], i)
+    ab_next = _pick(tab["alphas_cumprod_next"], i)
+    return x0 * torch.sqrt(ab_next) + torch.sqrt(1 - ab_next) * eps, x0
+
+
 def training_losses(sd, tab, tmap, x_start, t_idx, y, noise, style_eps, cond_drop, nj, nf, lambda_vel=1.0):
     """GaussianDiffusion.training_losses, LossType.HUBER (gaussian_diffusion.py:1249-1401): q_sample at the per-clip
     spaced indices t_idx, RAG.forward in training mode (cond_drop = the Bernoulli mask of mask_cond, RAG.py:84-93;

@@ -1051,3 +1051,31 @@ def test_error_paths_of_the_round2_entry_points():
     with pytest.raises(LsError):          # a single frame has no frame differences
         _cabi.huber_terms(torch.zeros(4, 1, device=DEV), torch.zeros(4, 1, device=DEV), None, None,
                           torch.zeros(3, device=DEV))
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_ddim_reverse_sample_vs_reference_fixture(name, golden_grad):
+    """ddim_reverse_sample (gaussian_diffusion.py:857-893), three steps up the deterministic ODE, against the reference's
+    outputs and the oracle on the recorded draws."""
+    dims, sd, cfg, diffusion = build(name, "ddim100")
+    B = 2
+    shape = (B, dims.njoints, dims.nfeats, 34)
+    tab, tmap = schedule_oracle.build("cosine", 1000, "ddim100")
+    tape = sampler_oracle.NoiseTape(seed=506)
+    yo = synthetic.synth_cond(dims, B)
+    xo = 0.5 * tape.draw(*shape)
+    want = []
+    for i in (10, 11, 12):
+        xo, _ = sampler_oracle.ddim_reverse_step(sd, tab, tmap, xo, i, yo, tape, dims.njoints, dims.nfeats)
+        want.append(xo)
+    diffusion.noise_source = cfg.noise_source = ls.ReplayNoise(tape.record)
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    x = 0.5 * diffusion.noise_source.randn(shape, DEV)
+    with torch.no_grad():
+        for k, i in enumerate((10, 11, 12)):
+            x = diffusion.ddim_reverse_sample(cfg, x, torch.tensor([i] * B, device=DEV), clip_denoised=False,
+                                              model_kwargs={"y": y})["sample"]
+            _close(x, golden_grad[name]["reverse_samples"][k])
+            _close(x, want[k])
+    with pytest.raises(AssertionError):
+        diffusion.ddim_reverse_sample(cfg, x, torch.tensor([5] * B, device=DEV), model_kwargs={"y": y}, eta=0.5)
