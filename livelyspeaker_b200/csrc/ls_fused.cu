@@ -846,8 +846,12 @@ __global__ void LS_CLUSTER_ATTR __launch_bounds__(NT_ALL, 1) fused_step_kernel(c
         epi_bar();
       }
       // Per-channel parameters used on the critical path (time embedding, LayerNorm-1 alpha / beta) are parked
-      // in thread-private shared-memory slots: with 219 KB of shared memory the L1 left over is too small to
-      // keep them, and an L2 round trip per M-tile inside the operand stores costs more than the stores.
+      // in shared-memory slots indexed by channel: with 219 KB of shared memory the L1 left over is too small to
+      // keep them, and an L2 round trip per M-tile inside the operand stores costs more than the stores.  The four
+      // warps that own a channel (rq = 0..3) all store the SAME value into its slot and each thread only reads after
+      // its own store, so no barrier is needed; a slot is rewritten for block l + 1 only after the token mix of block
+      // l, whose last MMA cannot start before all 16 warps have read the block-l value (racecheck, which does not see
+      // the ordering through the MMA, flags these stores; tools/README.md).
       {
         float er[4];
         float2 ab[4];
