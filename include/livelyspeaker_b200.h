@@ -139,7 +139,9 @@ int ls_wav_encoder(ls_handle* h, int32_t B, const float* audio, float* out, void
  * ls_precompute_cond.  t: ORIGINAL timesteps, one per clip.  uncond != 0 zeroes the
  * audio embedding (mask_cond force_mask, RAG.py:80-83).  style_eps [B,512] is the
  * randn of reparameterize (RAG.py:10-13).  out [B,J*D,F]; z_mu / z_logvar [B,512]
- * may be NULL.                                                                    */
+ * may be NULL.  On the tensor-core implementations this is the fused kernel
+ * (which always runs both guidance passes of a clip) with a per-clip combination
+ * weight of 1 (cond) / 0 (uncond); LS_IMPL_SIMT runs the single fp32 pass.          */
 int ls_model_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t,
                      int32_t uncond, const float* style_eps, float* out,
                      float* z_mu, float* z_logvar, void* stream);

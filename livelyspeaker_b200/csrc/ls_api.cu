@@ -307,13 +307,32 @@ extern "C" int ls_precompute_cond(ls_handle* h, int32_t B, const float* audio, f
   return LS_OK;
 }
 
+// One pass of RAG.forward.  On the tensor-core implementations it is the fused kernel in mode 2: the kernel always runs
+// both guidance passes of a clip (they share every weight block) and combines them as out_u + scale (out_c - out_u), so
+// scale = 0 returns the uncond pass exactly and scale = 1 the cond pass to within an ulp - 2x the arithmetic of a
+// single pass at 10x the speed of the fp32 CUDA-core kernel, which LS_IMPL_SIMT keeps as the exact-order path.
+static int forward_one_pass(ls_handle* h, int B, const float* x, const int64_t* t, int sel, const uint8_t* cond_drop,
+                            const float* style_eps, float* out, cudaStream_t s) {
+  const int impl = ls_get_impl(h);
+  if (impl == LS_IMPL_TC_BF16X3 || impl == LS_IMPL_TC_BF16) {
+    float* scale = h->out_c;          // [B] of a scratch buffer the tensor-core path does not use
+    int rc = lsk_pass_scale(h, B, sel == 1, cond_drop, scale, s);
+    if (rc) return rc;
+    ls_step_params p{};
+    p.mode = 2;
+    const ls_step_io io{style_eps, style_eps, nullptr, 0, 0, 0, nullptr, out};
+    return lsf_steps(h, B, 1, &p, &io, impl == LS_IMPL_TC_BF16X3, x, scale, s, t);
+  }
+  return lsk_denoise_simt(h, B, x, t, -1, sel, style_eps, style_eps, out, out, s, nullptr, cond_drop);
+}
+
 extern "C" int ls_model_forward(ls_handle* h, int32_t B, const float* x, const int64_t* t, int32_t uncond,
                                 const float* style_eps, float* out, float* z_mu, float* z_logvar, void* stream) {
   int rc = check_ready(h, B, true);
   if (rc) return rc;
   if (!x || !t || !style_eps || !out) return ls_fail(h, LS_EINVAL, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  if ((rc = lsk_denoise_simt(h, B, x, t, -1, uncond ? 2 : 1, style_eps, style_eps, out, out, s))) return rc;
+  if ((rc = forward_one_pass(h, B, x, t, uncond ? 2 : 1, nullptr, style_eps, out, s))) return rc;
   if (z_mu) LS_CUDA(h, cudaMemcpyAsync(z_mu, h->z_mu, (size_t)B * LS_D * 4, cudaMemcpyDeviceToDevice, s));
   if (z_logvar) LS_CUDA(h, cudaMemcpyAsync(z_logvar, h->z_lv, (size_t)B * LS_D * 4, cudaMemcpyDeviceToDevice, s));
   return LS_OK;
@@ -325,7 +344,7 @@ extern "C" int ls_model_forward_train(ls_handle* h, int32_t B, const float* x, c
   if (rc) return rc;
   if (!x || !t || !style_eps || !out) return ls_fail(h, LS_EINVAL, "null argument");
   cudaStream_t s = (cudaStream_t)stream;
-  if ((rc = lsk_denoise_simt(h, B, x, t, -1, 1, style_eps, style_eps, out, out, s, nullptr, cond_drop))) return rc;
+  if ((rc = forward_one_pass(h, B, x, t, 1, cond_drop, style_eps, out, s))) return rc;
   if (z_mu) LS_CUDA(h, cudaMemcpyAsync(z_mu, h->z_mu, (size_t)B * LS_D * 4, cudaMemcpyDeviceToDevice, s));
   if (z_logvar) LS_CUDA(h, cudaMemcpyAsync(z_logvar, h->z_lv, (size_t)B * LS_D * 4, cudaMemcpyDeviceToDevice, s));
   return LS_OK;

@@ -128,6 +128,7 @@ int lsk_cfg_update(ls_handle* h, int B, const ls_step_params* p, const float* ou
                    float* x_prev, float* pred_x0, cudaStream_t s);
 int lsk_axpby(ls_handle* h, int64_t n, const float* a, const float* b, float ca, float cb, float* out,
               cudaStream_t s);
+int lsk_pass_scale(ls_handle* h, int B, int cond, const uint8_t* drop, float* scale, cudaStream_t s);
 // ls_wavenc_tc.cu
 int lsw_init(ls_handle* h, const float* const w[3], cudaStream_t s, const float* w0 = nullptr);   // w0: layer-1 weights
 void lsw_destroy(ls_handle* h);

@@ -62,3 +62,15 @@ int lsk_axpby(ls_handle* h, int64_t n, const float* a, const float* b, float ca,
   LS_LAUNCH_CHECK(h);
   return LS_OK;
 }
+
+// scale[b] that makes the guided combination out_u + scale (out_c - out_u) return ONE pass: 1 = cond, 0 = uncond;
+// per clip 1 - (drop[b] != 0) when a training-mode condition-dropout mask is given (RAG.py:84-93)
+__global__ void pass_scale_kernel(int B, int cond, const uint8_t* __restrict__ drop, float* __restrict__ scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) scale[b] = drop != nullptr ? (drop[b] != 0 ? 0.f : 1.f) : (cond ? 1.f : 0.f);
+}
+int lsk_pass_scale(ls_handle* h, int B, int cond, const uint8_t* drop, float* scale, cudaStream_t s) {
+  pass_scale_kernel<<<(B + 255) / 256, 256, 0, s>>>(B, cond, drop, scale);
+  LS_LAUNCH_CHECK(h);
+  return LS_OK;
+}
