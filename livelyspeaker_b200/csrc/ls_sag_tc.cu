@@ -60,13 +60,17 @@ __global__ void sag_cross_fold_kernel(ls_sag_layer L, float* __restrict__ wct, f
   else
     bc[n] = (float)(a + (double)L.ca_out_b[n]);
 }
-constexpr int CA_CLIPS = 16;
-__global__ void __launch_bounds__(128) sag_cross_kernel(const float* __restrict__ wct, const float* __restrict__ bc,
+constexpr int CA_CLIPS = 8;
+// block = 8 clips x 128 output columns of one layer; 512 threads = 128 columns x 4 slices of K (the loop is a chain
+// of L2 round trips for the weights: four times shorter per thread, 16 loads in flight), partial sums through shared memory
+__global__ void __launch_bounds__(512) sag_cross_kernel(const float* __restrict__ wct, const float* __restrict__ bc,
                                                         const float* __restrict__ z, int B, float* __restrict__ ca) {
   __shared__ __align__(16) float zs[CA_CLIPS][D];
-  const int l = blockIdx.z, b0 = blockIdx.x * CA_CLIPS, n = blockIdx.y * 128 + threadIdx.x;
+  __shared__ float red[4][CA_CLIPS][128];
+  const int l = blockIdx.z, b0 = blockIdx.x * CA_CLIPS, col = threadIdx.x & 127, ks = threadIdx.x >> 7;
+  const int n = blockIdx.y * 128 + col;
 #pragma unroll
-  for (int i = threadIdx.x; i < CA_CLIPS * D / 4; i += 128) {      // 16 independent float4 loads per thread
+  for (int i = threadIdx.x; i < CA_CLIPS * D / 4; i += 512) {
     const int e = 4 * i;
     *reinterpret_cast<float4*>(&zs[e >> 9][e & 511]) = (b0 + (e >> 9) < B) ? *reinterpret_cast<const float4*>(z + (size_t)b0 * D + e)
                                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -76,16 +80,21 @@ __global__ void __launch_bounds__(128) sag_cross_kernel(const float* __restrict_
   float a[CA_CLIPS];
 #pragma unroll
   for (int i = 0; i < CA_CLIPS; ++i) a[i] = 0.f;
-#pragma unroll 8
-  for (int k = 0; k < D; ++k) {
+#pragma unroll 16
+  for (int k = ks * 128; k < ks * 128 + 128; ++k) {
     const float wv = wl[(size_t)k * D];
 #pragma unroll
     for (int i = 0; i < CA_CLIPS; ++i) a[i] = fmaf(zs[i][k], wv, a[i]);
   }
-  const float bo = bc[l * D + n];
 #pragma unroll
-  for (int i = 0; i < CA_CLIPS; ++i)
-    if (b0 + i < B) ca[((size_t)l * B + b0 + i) * D + n] = a[i] + bo;
+  for (int i = 0; i < CA_CLIPS; ++i) red[ks][i][col] = a[i];
+  __syncthreads();
+  if (ks == 0) {
+    const float bo = bc[l * D + n];
+#pragma unroll
+    for (int i = 0; i < CA_CLIPS; ++i)
+      if (b0 + i < B) ca[((size_t)l * B + b0 + i) * D + n] = ((red[0][i][col] + red[1][i][col]) + (red[2][i][col] + red[3][i][col])) + bo;
+  }
 }
 
 // one (clip, head): O[t][e] = sum_s softmax_s(q_t . k_s / sqrt(128)) v[s][e]; thread = e
@@ -176,9 +185,21 @@ __global__ void __launch_bounds__(256) sag_final_kernel(ls_sag_weights w, const 
   }
   for (int j0 = 0; j0 < JD; j0 += FIN_J) {
     __syncthreads();
-    for (int i = threadIdx.x; i < FIN_J * D; i += 256) {       // fin_wt is [k][JD]: 32 consecutive j per k
-      const int k = i >> 5, jj = i & 31;
-      ws[jj * (D + 1) + k] = (j0 + jj < JD) ? w.fin_wt[(size_t)k * JD + j0 + jj] : 0.f;
+    // fin_wt is [k][JD]: 32 consecutive j per k.  64 loads per thread, 16 in flight at a time (one at a time the loop
+    // was 64 serialised L2 round trips: 50 of the kernel's 90 us)
+#pragma unroll 4
+    for (int i0 = 0; i0 < FIN_J * D; i0 += 16 * 256) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = i0 + u * 256 + threadIdx.x, k = i >> 5, jj = i & 31;
+        v[u] = (j0 + jj < JD) ? w.fin_wt[(size_t)k * JD + j0 + jj] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int i = i0 + u * 256 + threadIdx.x, k = i >> 5, jj = i & 31;
+        ws[jj * (D + 1) + k] = v[u];
+      }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < FIN_J * T; i += 256) {
@@ -301,7 +322,7 @@ extern "C" int ls_sag_decode_tc(ls_sag* s, int32_t B, const float* x, const floa
   // LS_SAG_MASK (diagnostic, tools/sag_bench.py): bit i = launch kernel kind i, to time the kinds one by one
   static const int kmask = getenv("LS_SAG_MASK") ? atoi(getenv("LS_SAG_MASK")) : 0xFF;
   if (kmask & 1) sag_queries_kernel<<<B, 512, 0, st>>>(w, x, s->X);
-  if (kmask & 2) sag_cross_kernel<<<dim3((B + CA_CLIPS - 1) / CA_CLIPS, D / 128, w.n_layers), 128, 0, st>>>(s->wct, s->bc, z, B, s->CA);
+  if (kmask & 2) sag_cross_kernel<<<dim3((B + CA_CLIPS - 1) / CA_CLIPS, D / 128, w.n_layers), 512, 0, st>>>(s->wct, s->bc, z, B, s->CA);
   s->launches += 2;
   for (int l = 0; l < w.n_layers; ++l) {
     const ls_sag_layer& L = w.layer[l];
