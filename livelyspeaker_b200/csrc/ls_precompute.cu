@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(512) cond_proj_kernel(LsWeights w, int JD, int
   }
 
   float pre[LS_NPRE] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 9
   for (int j = 0; j < JD; ++j) {
     const float wv = w.w_o_t[(size_t)j * LS_D + c];
 #pragma unroll
@@ -249,7 +250,8 @@ __global__ void __launch_bounds__(512) cond_proj_kernel(LsWeights w, int JD, int
   for (int f = 0; f < LS_F; ++f) Pb[f * LS_D + c] = (f < LS_NPRE) ? (pre[f] + wbit) + bin : bin;
 
   float mu = 0.f, lv = 0.f;
-  for (int k = 0; k < LS_SPK; ++k) {
+#pragma unroll 16
+  for (int k = 0; k < LS_SPK; ++k) {          // 16 x 2 weight loads in flight (one pair at a time: 256 L2 round trips)
     const float zv = z_s[k];
     mu = fmaf(zv, w.w_mu_t[(size_t)k * LS_D + c], mu);
     lv = fmaf(zv, w.w_lv_t[(size_t)k * LS_D + c], lv);
