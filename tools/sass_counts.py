@@ -12,7 +12,7 @@ name, counts, total = None, {}, 0
 def flush():
     if name:
         demangled = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
-        short = re.sub(r"\(.*", "", demangled).replace("(anonymous namespace)::", "")[:90]
+        short = re.sub(r"\(.*", "", demangled.replace("(anonymous namespace)::", ""))[:90]
         print("%-92s total=%6d  %s" % (short, total, "  ".join("%s=%d" % (k, counts[k]) for k in KEYS if counts.get(k))))
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
