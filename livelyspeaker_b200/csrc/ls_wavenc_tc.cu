@@ -360,7 +360,7 @@ struct Lay2 {
   static constexpr uint32_t STAGE = 2 * A_IMG + 2 * B_IMG;
   static constexpr uint32_t RAW_ROW = 784;                             // floats per staged input channel (778 used)
   static constexpr uint32_t OFF_RAW = 2 * STAGE;
-  static constexpr uint32_t OFF_WPART = OFF_RAW + CI_PER_CHUNK * RAW_ROW * 4;     // [4 warps][2 * CO] epilogue partials
+  static constexpr uint32_t OFF_WPART = OFF_RAW + 8 * CI_PER_CHUNK * 108 * 4;     // 8 warps x 4 channels x 108 floats; then [4 warps][2 * CO] epilogue partials
   static constexpr uint32_t OFF_BARS = OFF_WPART + 4 * 2 * CO * 4;
   static constexpr uint32_t SMEM = OFF_BARS + 64 + 1024;
 };
@@ -445,21 +445,24 @@ __global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __res
     umma_commit_s_elect(bars_s + 8 * ACC);
   } else {
     // ================= builders, then the epilogue ====================================================
-    const uint32_t row_off = (uint32_t)(pos >> 3) * 1024u + (uint32_t)(pos & 7) * 128u;
-    // the tile's input window: 127 * 6 + 16 samples per channel from w0, clipped at the end of the row
-    constexpr int WIN = 127 * STRIDE + 16;
-    const int w0 = lo0 * STRIDE, n_ok = min(WIN, Li - w0);
+    // Warp w builds tile positions 16 w .. 16 w + 15 from ITS OWN window of the input (samples 96 w .. 96 w + 105 of
+    // each channel, staged in a private 112-float row): no block barrier in the loop, only __syncwarp, so the eight
+    // warps drift apart and hide each other's latencies (two block barriers per chunk cost 300 of 1500 cycles and kept
+    // the warps in lock step).  Adjacent warps re-read 10 of 106 samples.
+    constexpr int WWIN = 15 * STRIDE + 16;            // 106
+    constexpr int WROW = 108;                         // floats per staged channel row of a warp (keeps 2 CTAs per SM at CO = 64)
+    float* wraw = raw + warp * (CI_PER_CHUNK * WROW);
+    const int w0 = (lo0 + 16 * warp) * STRIDE, n_ok = min(WWIN, Li - w0);      // may be <= 0 past the end of the row
     const float* inb = in + (size_t)b * Ci * Li + w0;
     const float2* stb = in_stats + (size_t)b * Ci;
-    constexpr int PER_T = (WIN + 255) / 256;          // 4 samples per thread per channel
-    float nx[CI_PER_CHUNK][PER_T];
-    auto load_raw = [&](int c) {                      // coalesced: consecutive threads, consecutive samples
+    float nx[CI_PER_CHUNK][4];
+    auto load_raw = [&](int c) {                      // coalesced: consecutive lanes, consecutive samples
 #pragma unroll
       for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
         const float* src = inb + (size_t)(c * CI_PER_CHUNK + cil) * Li;
 #pragma unroll
-        for (int i = 0; i < PER_T; ++i) {
-          const int idx = tid + 256 * i;
+        for (int i = 0; i < 4; ++i) {
+          const int idx = lane + 32 * i;
           nx[cil][i] = idx < n_ok ? __ldg(src + idx) : 0.f;
         }
       }
@@ -469,17 +472,17 @@ __global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __res
     for (int c = 0; c < n_chunks; ++c) {
       const int s = c & 1;
       uint8_t* stage = sm + s * L::STAGE;
-      // normalise (InstanceNorm of the previous layer) + LeakyReLU once per element, into the staging rows
+      // normalise (InstanceNorm of the previous layer) + LeakyReLU once per element, into the warp's staging rows
 #pragma unroll
       for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
         const float2 st = __ldg(stb + c * CI_PER_CHUNK + cil);
 #pragma unroll
-        for (int i = 0; i < PER_T; ++i) {
-          const int idx = tid + 256 * i;
-          if (idx < (int)L::RAW_ROW) {
+        for (int i = 0; i < 4; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < WROW) {
             float v = (nx[cil][i] - st.x) * st.y;
             v = v > 0.f ? v : 0.3f * v;
-            raw[cil * L::RAW_ROW + idx] = idx < n_ok ? v : 0.f;      // finite padding: tap 15 meets a zero weight
+            wraw[cil * WROW + idx] = idx < n_ok ? v : 0.f;          // finite padding: tap 15 meets a zero weight
           }
         }
       }
@@ -487,34 +490,32 @@ __global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __res
       if (c >= 2) {                                   // the MMAs that read this stage (chunk c-2) are done
         mbar_wait(&bars[EMPTY0 + s], ((c >> 1) - 1) & 1);
       }
-      builders_bar();                                 // staging rows complete
+      __syncwarp();                                   // the warp's staging rows are complete
 #pragma unroll
-      for (int cc = 0; cc < CI_PER_CHUNK / 2; ++cc) {
-        const int cil = 2 * half + cc;
-        const float2* wr = reinterpret_cast<const float2*>(raw + cil * L::RAW_ROW + pos * STRIDE);
-        float v[16];
+      for (int i = 0; i < 4; ++i) {                   // 16 positions x 4 channels x 2 halves = 128 units of 8 samples
+        const int u = lane + 32 * i, pl = u & 15, cil = (u >> 4) & 3, hh = u >> 6;
+        const int row = 16 * warp + pl;
+        const float2* wr = reinterpret_cast<const float2*>(wraw + cil * WROW + pl * STRIDE + 8 * hh);
+        const bool ok = lo0 + row < Lo;
+        float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 t = valid ? wr[i] : make_float2(0.f, 0.f);
-          v[2 * i] = t.x;
-          v[2 * i + 1] = t.y;
+        for (int q = 0; q < 4; ++q) {
+          const float2 t = ok ? wr[q] : make_float2(0.f, 0.f);
+          v[2 * q] = t.x;
+          v[2 * q + 1] = t.y;
         }
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint4 hi, lw;
-          hi.x = pack_hi_lo(v[8 * hh + 0], v[8 * hh + 1], &lw.x);
-          hi.y = pack_hi_lo(v[8 * hh + 2], v[8 * hh + 3], &lw.y);
-          hi.z = pack_hi_lo(v[8 * hh + 4], v[8 * hh + 5], &lw.z);
-          hi.w = pack_hi_lo(v[8 * hh + 6], v[8 * hh + 7], &lw.w);
-          const uint32_t off = row_off + ((uint32_t)((cil * 2 + hh) ^ (pos & 7)) << 4);
-          *reinterpret_cast<uint4*>(stage + off) = hi;
-          *reinterpret_cast<uint4*>(stage + A_IMG + off) = lw;
-        }
+        uint4 hi, lw;
+        hi.x = pack_hi_lo(v[0], v[1], &lw.x);
+        hi.y = pack_hi_lo(v[2], v[3], &lw.y);
+        hi.z = pack_hi_lo(v[4], v[5], &lw.z);
+        hi.w = pack_hi_lo(v[6], v[7], &lw.w);
+        const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + ((uint32_t)((cil * 2 + hh) ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(stage + off) = hi;
+        *reinterpret_cast<uint4*>(stage + A_IMG + off) = lw;
       }
       fence_proxy_async_smem();
-      __syncwarp();
+      __syncwarp();                                   // also: every lane is done with the staging rows
       if (lane == 0) mbar_arrive(&bars[A_FULL0 + s]);
-      builders_bar();                                 // every builder is done with the staging rows
     }
     mbar_wait(&bars[ACC], 0);
     __syncwarp();
