@@ -476,13 +476,15 @@ __global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __res
 #pragma unroll
       for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
         const float2 st = __ldg(stb + c * CI_PER_CHUNK + cil);
+        const float sc = st.y, sh = -st.x * st.y;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int idx = lane + 32 * i;
           if (idx < WROW) {
-            float v = (nx[cil][i] - st.x) * st.y;
-            v = v > 0.f ? v : 0.3f * v;
-            wraw[cil * WROW + idx] = idx < n_ok ? v : 0.f;          // finite padding: tap 15 meets a zero weight
+            // Samples past the end of the row (loaded as 0) only meet the zero weight of the 16th tap or belong to
+            // positions >= Lo, whose accumulator rows are never read: any finite value will do, no select needed.
+            const float v = fmaf(nx[cil][i], sc, sh);
+            wraw[cil * WROW + idx] = fmaxf(v, 0.3f * v);
           }
         }
       }
@@ -496,11 +498,10 @@ __global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __res
         const int u = lane + 32 * i, pl = u & 15, cil = (u >> 4) & 3, hh = u >> 6;
         const int row = 16 * warp + pl;
         const float2* wr = reinterpret_cast<const float2*>(wraw + cil * WROW + pl * STRIDE + 8 * hh);
-        const bool ok = lo0 + row < Lo;
-        float v[8];
+        float v[8];                                   // rows of positions >= Lo hold finite leftovers: their outputs are masked
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float2 t = ok ? wr[q] : make_float2(0.f, 0.f);
+          const float2 t = wr[q];
           v[2 * q] = t.x;
           v[2 * q + 1] = t.y;
         }
