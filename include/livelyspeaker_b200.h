@@ -292,6 +292,30 @@ int ls_huber_terms(int64_t rows, int32_t n_frames, const float* target, const fl
                    int64_t n_z, const float* z_mu, const float* z_logvar, float* terms,
                    int32_t device, void* stream);
 
+/* ---- latent features of the evaluation's pose autoencoder (FGD features) ----------------
+ * scripts/model/embedding_net.py:40-79 (PoseEncoderConv.forward in eval mode) as called by
+ * scripts/model/ted_evaluator.py:35-41 (EmbeddingSpaceEvaluator.push_samples).  All pointers are DEVICE fp32.
+ * Convolution weights keep torch's [out][in][k] layout; the linear weights are TRANSPOSED ([in][out]); every
+ * BatchNorm (running statistics) is folded by the host to y = scale * x + shift per channel, applied after the bias.
+ * slope_conv / slope_fc are the negative slopes of the LeakyReLUs of the two stacks (0.2 and - because the reference
+ * writes nn.LeakyReLU(True) - 1.0).                                                                            */
+typedef struct ls_pose_encoder_weights {
+  int32_t pose_dim, n_frames;                 /* n_frames must be 34: the first linear layer is 384 = 32 x 12 wide */
+  float slope_conv, slope_fc;
+  const float *c1_w, *c1_b, *c1_scale, *c1_shift;   /* net.0: Conv1d(pose_dim, 32, 3) + BatchNorm1d(32)          */
+  const float *c2_w, *c2_b, *c2_scale, *c2_shift;   /* net.1: Conv1d(32, 64, 3) + BatchNorm1d(64)                */
+  const float *c3_w, *c3_b, *c3_scale, *c3_shift;   /* net.2: Conv1d(64, 64, 4, stride 2) + BatchNorm1d(64)      */
+  const float *c4_w, *c4_b;                         /* net.3: Conv1d(64, 32, 3)                                  */
+  const float *f1_wt, *f1_b, *f1_scale, *f1_shift;  /* out_net.0/1: Linear(384, 256) + BatchNorm1d(256)          */
+  const float *f2_wt, *f2_b, *f2_scale, *f2_shift;  /* out_net.3/4: Linear(256, 128) + BatchNorm1d(128)          */
+  const float *f3_wt, *f3_b;                        /* out_net.6: Linear(128, 32)                                */
+  const float *mu_wt, *mu_b, *lv_wt, *lv_b;         /* fc_mu, fc_logvar: Linear(32, 32)                          */
+} ls_pose_encoder_weights;
+/* poses [B][n_frames][pose_dim] (device, the layout push_samples receives) -> mu [B][32] and, when not NULL,
+ * logvar [B][32] (device).  Stateless; errors through ls_last_error(NULL).                                     */
+int ls_pose_features(const ls_pose_encoder_weights* w, int32_t B, const float* poses, float* mu, float* logvar,
+                     int32_t device, void* stream);
+
 /* Introspection used by tests / bench: number of kernels launched by this handle
  * since creation, and read-back of the step-invariant buffers.                    */
 int64_t ls_launch_count(const ls_handle* h);

@@ -21,7 +21,7 @@ EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_loa
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
            "ls_model_forward", "ls_model_forward_train", "ls_huber_terms", "ls_cfg_forward", "ls_cfg_forward_grad", "ls_cfg_backward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_sag_create", "ls_sag_decode_tc",
            "ls_sag_launch_count", "ls_sag_destroy", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
-           "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align"]
+           "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align", "ls_pose_features"]
 
 
 class LsConfig(ctypes.Structure):

@@ -5,7 +5,7 @@ Mirrors the body of ``infer_from_testloader`` between the sampler call and the s
 beat alignment score against audio onset times.  The arithmetic runs in two small CUDA kernels behind the C ABI
 (``ls_motion_beats`` / ``ls_beat_align``) on the sampler's output where it lies; there is no CPU path (``LsError``).
 The onset detector (``librosa.onset.onset_detect``, :113) stays with the caller: pass its result as ``audio_beat_times``.
-The FGD / diversity scores need the private evaluation checkpoints and are out of scope.
+The FGD / feature-distance / diversity scores of the same script live in ``ted_evaluator.py`` / ``embedding_net.py``.
 """
 import ctypes
 from ctypes import c_float, c_int32, c_void_p

@@ -148,6 +148,58 @@ def synth_sag_state_dict(seed=3, njoints=9, nfeats=3, d=512, ff=1024, layers=3):
     return sd
 
 
+def synth_embed_state_dict(seed=5, pose_dim=27):
+    """Deterministic state_dict with the key set of the evaluation's EmbeddingNet(pose_dim, 34)
+    (scripts/model/embedding_net.py:40-64, 166-216, 266-270 - the `gen_dict` of the autoencoder checkpoint
+    scripts/model/ted_evaluator.py:16-20 loads), BatchNorm running statistics away from their defaults."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def uni(shape, fan_in):
+        b = 1.0 / math.sqrt(fan_in)
+        return (torch.rand(shape, generator=g) * 2 - 1) * b
+
+    def layer(name, shape):
+        fan_in = 1
+        for n in shape[1:]:
+            fan_in *= n
+        sd[name + ".weight"] = uni(shape, fan_in) * math.sqrt(3.0)
+        sd[name + ".bias"] = uni((shape[0],), fan_in)
+
+    def bn(name, c):
+        sd[name + ".weight"] = 1 + 0.2 * torch.randn(c, generator=g)
+        sd[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
+        sd[name + ".running_mean"] = 0.2 * torch.randn(c, generator=g)
+        sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+        sd[name + ".num_batches_tracked"] = torch.tensor(1000, dtype=torch.int64)
+
+    e = "pose_encoder."
+    for i, shape in enumerate(((32, pose_dim, 3), (64, 32, 3), (64, 64, 4))):
+        layer(e + "net.%d.0" % i, shape)
+        bn(e + "net.%d.1" % i, shape[0])
+    layer(e + "net.3", (32, 64, 3))
+    layer(e + "out_net.0", (256, 384))
+    bn(e + "out_net.1", 256)
+    layer(e + "out_net.3", (128, 256))
+    bn(e + "out_net.4", 128)
+    layer(e + "out_net.6", (32, 128))
+    layer(e + "fc_mu", (32, 32))
+    layer(e + "fc_logvar", (32, 32))
+    d = "decoder."
+    layer(d + "pre_net.0", (64, 32))
+    bn(d + "pre_net.1", 64)
+    layer(d + "pre_net.3", (136, 64))
+    sd[d + "net.0.weight"] = uni((4, 32, 3), 12)           # ConvTranspose1d: [in, out, k]
+    sd[d + "net.0.bias"] = uni((32,), 12)
+    bn(d + "net.1", 32)
+    sd[d + "net.3.weight"] = uni((32, 32, 3), 96)
+    sd[d + "net.3.bias"] = uni((32,), 96)
+    bn(d + "net.4", 32)
+    layer(d + "net.6", (32, 32, 3))
+    layer(d + "net.7", (pose_dim, 32, 3))
+    return sd
+
+
 def synth_cond(dims, batch, seed=233, scale=1.5, device="cpu"):
     """The `y` dict the eval scripts build (scripts/test_RAG_ted.py:63-70,
     scripts_beat/test_RAG_beat.py:100-125), synthetic values."""

@@ -71,5 +71,10 @@ def golden_train():
 
 
 @pytest.fixture(scope="session")
+def golden_fgd():
+    return dict(np.load(os.path.join(GOLDEN, "fgd.npz")))
+
+
+@pytest.fixture(scope="session")
 def golden_metrics():
     return dict(np.load(os.path.join(GOLDEN, "metrics.npz")))

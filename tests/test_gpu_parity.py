@@ -805,6 +805,74 @@ def test_rhythm_metric_on_device(golden_metrics):
         metrics.motion_beats(out.cpu())
 
 
+def test_fgd_features_and_scores_on_device(golden_fgd, tmp_path):
+    """ls_pose_features (FGD features) against the fixture made by the reference's EmbeddingNet and
+    EmbeddingSpaceEvaluator and against the oracle; ragged batches (the kernel packs 4 clips per CTA); the whole
+    evaluator flow (checkpoint -> push_samples on device tensors -> get_scores / get_diversity_scores)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import fgd_cases as fc
+    from livelyspeaker_b200 import ted_evaluator
+    from oracle import evaluator_oracle
+    sd = synthetic.synth_embed_state_dict(seed=fc.SEED_WEIGHTS, pose_dim=fc.POSE_DIM)
+    path = str(tmp_path / "gesture_autoencoder_checkpoint_best.bin")
+    torch.save({"pose_dim": fc.POSE_DIM, "gen_dict": sd}, path)
+    ev = ted_evaluator.EmbeddingSpaceEvaluator(path)
+    worst = 0.0
+    for i, (generated, real) in enumerate(fc.pose_batches()):
+        ev.push_samples(generated.to(DEV), real.to(DEV))
+        for tag, poses, got in (("gen", generated, ev.generated_feat_list[-1]), ("real", real, ev.real_feat_list[-1])):
+            np.testing.assert_allclose(got, golden_fgd["mu_%s_%d" % (tag, i)], rtol=RTOL, atol=ATOL)
+            worst = max(worst, float(np.abs(got - golden_fgd["mu_%s_%d" % (tag, i)]).max()))
+            z, mu, logvar = ev.net(poses.to(DEV))
+            assert z is mu
+            np.testing.assert_allclose(logvar.cpu().numpy(), golden_fgd["logvar_%s_%d" % (tag, i)], rtol=RTOL, atol=ATOL)
+    print("FGD features: max |gpu - reference| = %.3g" % worst)
+    frechet, feat_dist = ev.get_scores()
+    assert abs(frechet - float(golden_fgd["frechet"])) < 1e-4 * max(1.0, float(golden_fgd["frechet"]))
+    assert abs(feat_dist - float(golden_fgd["feat_dist"])) < 1e-4
+    torch.manual_seed(fc.DIVERSITY_SEED)
+    assert abs(ev.get_diversity_scores() - float(golden_fgd["diversity"])) < 1e-4
+    # ragged batches against the oracle: 1, 3, 4, 5, 67 clips
+    g = torch.Generator().manual_seed(9)
+    for B in (1, 3, 4, 5, 67):
+        poses = 0.3 * torch.randn(B, 34, fc.POSE_DIM, generator=g)
+        _, mu, logvar = ev.net(poses.to(DEV))
+        o_mu, o_lv = evaluator_oracle.pose_features(sd, poses)
+        np.testing.assert_allclose(mu.cpu().numpy(), o_mu.numpy(), rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(logvar.cpu().numpy(), o_lv.numpy(), rtol=RTOL, atol=ATOL)
+    # variational encoding: one randn_like draw of the global (CUDA) generator, embedding_net.py:9-12
+    poses = poses.to(DEV)
+    torch.manual_seed(5)
+    z, mu, logvar = ev.net(poses, variational_encoding=True)
+    torch.manual_seed(5)
+    std = torch.exp(0.5 * logvar)
+    assert torch.equal(z, mu + torch.randn_like(std) * std)
+    # another pose dimension (BEAT-sized vectors would be 141 wide and do not fit: loud error, not a wrong answer)
+    with pytest.raises(ValueError):
+        ev.net(torch.zeros(2, 30, fc.POSE_DIM, device=DEV))
+    from livelyspeaker_b200 import embedding_net
+    big = embedding_net.EmbeddingNet(141, 34).eval()
+    with pytest.raises(ls.LsError):
+        big(torch.zeros(2, 34, 141, device=DEV))
+    # end of the drop-in flow (scripts/test_RAG_ted.py:84-86): sampler output -> aligned_motions -> push_samples
+    dims, _sd, cfg, diffusion = build("ted", "ddim100")
+    B = 64
+    y = synthetic.synth_cond(dims, B, device=DEV)
+    torch.manual_seed(3)
+    sample = diffusion.ddim_sample_loop(cfg, (B, 9, 3, 34), clip_denoised=False, model_kwargs={"y": y}, skip_timesteps=90)
+    vec_seq = y["origin_x"].permute(0, 3, 1, 2).reshape(B, 34, -1)
+    aligned = sample.permute(0, 3, 1, 2).reshape(B, 34, -1)
+    ev.reset()
+    ev.push_samples(aligned, vec_seq)
+    o_mu, _ = evaluator_oracle.pose_features(sd, aligned.cpu())
+    np.testing.assert_allclose(ev.generated_feat_list[0], o_mu.numpy(), rtol=RTOL, atol=ATOL)
+    frechet, feat_dist = ev.get_scores()
+    o_frechet, o_feat = evaluator_oracle.scores([o_mu.numpy()], [evaluator_oracle.pose_features(sd, vec_seq.cpu())[0].numpy()])
+    assert abs(frechet - o_frechet) < 1e-3 * max(1.0, abs(o_frechet)) and abs(feat_dist - o_feat) < 1e-3
+
+
 # ---- *_with_grad samplers: differentiable model call = ls_cfg_forward_grad / ls_cfg_backward -------------------------
 def _grad_cases():
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))

@@ -260,6 +260,76 @@ def test_rhythm_metric_oracle(golden_metrics):
     assert float(g["sigma"]) == metrics.SIGMA
 
 
+def _fgd_cases():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import fgd_cases
+    return fgd_cases
+
+
+def test_fgd_oracle_vs_reference_fixture(golden_fgd):
+    """oracle/evaluator_oracle.py against the fixture the reference's EmbeddingNet + EmbeddingSpaceEvaluator produced
+    (tests/golden/make_golden_fgd.py): features of every pushed batch, Frechet distance, feature distance, diversity."""
+    from oracle import evaluator_oracle
+    fc = _fgd_cases()
+    sd = synthetic.synth_embed_state_dict(seed=fc.SEED_WEIGHTS, pose_dim=fc.POSE_DIM)
+    assert abs(sum(float(v.double().abs().sum()) for v in sd.values()) - float(golden_fgd["weights_abs_sum"])) < 1e-6
+    gen, real = [], []
+    for i, (generated, real_poses) in enumerate(fc.pose_batches()):
+        for tag, poses, keep in (("gen", generated, gen), ("real", real_poses, real)):
+            mu, logvar = evaluator_oracle.pose_features(sd, poses)
+            np.testing.assert_allclose(mu.numpy(), golden_fgd["mu_%s_%d" % (tag, i)], rtol=1e-5, atol=5e-6)
+            np.testing.assert_allclose(logvar.numpy(), golden_fgd["logvar_%s_%d" % (tag, i)], rtol=1e-5, atol=5e-6)
+            keep.append(golden_fgd["mu_%s_%d" % (tag, i)])
+    frechet, feat_dist = evaluator_oracle.scores(gen, real)
+    assert abs(frechet - float(golden_fgd["frechet"])) < 1e-9 and abs(feat_dist - float(golden_fgd["feat_dist"])) < 1e-6
+    torch.manual_seed(fc.DIVERSITY_SEED)
+    assert abs(evaluator_oracle.diversity(gen) - float(golden_fgd["diversity"])) < 1e-6
+
+
+def test_fgd_host_statistics_and_surface(golden_fgd, tmp_path):
+    """The product's EmbeddingSpaceEvaluator: checkpoint contract of the constructor (ted_evaluator.py:14-24), the
+    reference's key set (the synthetic gen_dict loaded strictly into the reference module when the fixture was made),
+    host-side statistics on the fixture's features, closed-form Frechet cases, and no CPU path for the encoder."""
+    from livelyspeaker_b200 import ted_evaluator, embedding_net
+    from livelyspeaker_b200._cabi import LsError
+    fc = _fgd_cases()
+    sd = synthetic.synth_embed_state_dict(seed=fc.SEED_WEIGHTS, pose_dim=fc.POSE_DIM)
+    net = embedding_net.EmbeddingNet(fc.POSE_DIM, 34)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    path = str(tmp_path / "gesture_autoencoder_checkpoint_best.bin")
+    torch.save({"pose_dim": fc.POSE_DIM, "gen_dict": sd}, path)
+    ev = ted_evaluator.EmbeddingSpaceEvaluator(path)
+    assert ev.pose_dim == fc.POSE_DIM and not ev.net.training and not any(p.requires_grad for p in ev.net.parameters())
+    assert float(ev.net.pose_encoder.out_net[2].negative_slope) == 1.0        # nn.LeakyReLU(True), embedding_net.py:54
+    generated, real_poses = fc.pose_batches()[0]
+    with pytest.raises(LsError):
+        ev.push_samples(generated, real_poses)                               # host tensors: no CPU implementation
+    with pytest.raises(NotImplementedError):
+        ev.net.train()(generated)
+    with pytest.raises(NotImplementedError):
+        ev.net.decoder(torch.zeros(1, 32))
+    for i in range(fc.N_BATCHES):
+        ev.generated_feat_list.append(golden_fgd["mu_gen_%d" % i])
+        ev.real_feat_list.append(golden_fgd["mu_real_%d" % i])
+    frechet, feat_dist = ev.get_scores()
+    assert abs(frechet - float(golden_fgd["frechet"])) < 1e-9 and abs(feat_dist - float(golden_fgd["feat_dist"])) < 1e-6
+    torch.manual_seed(fc.DIVERSITY_SEED)
+    assert abs(ev.get_diversity_scores() - float(golden_fgd["diversity"])) < 1e-6
+    assert ev.get_no_of_samples() == fc.N_BATCHES
+    ev.reset()
+    assert ev.get_no_of_samples() == 0 and ev.generated_feat_list == []
+    # closed forms: identical Gaussians -> 0; commuting diagonal covariances -> |dmu|^2 + sum (sqrt a - sqrt b)^2
+    f = ted_evaluator.EmbeddingSpaceEvaluator.calculate_frechet_distance
+    a, b = np.array([1.0, 4.0, 9.0]), np.array([4.0, 1.0, 16.0])
+    assert abs(f(np.zeros(3), np.diag(a), np.zeros(3), np.diag(a))) < 1e-9
+    want = 3 * 0.25 + float(np.sum((np.sqrt(a) - np.sqrt(b)) ** 2))
+    assert abs(f(np.full(3, 0.5), np.diag(a), np.zeros(3), np.diag(b)) - want) < 1e-9
+    with pytest.raises(AssertionError):
+        f(np.zeros(3), np.eye(3), np.zeros(2), np.eye(2))
+
+
 @pytest.mark.parametrize("tag", ["anc_lo_clip", "ddim_eta_lo"])
 def test_oracle_with_grad_samplers_vs_reference_fixture(tag):
     """The oracle's p_sample_with_grad / ddim_sample_with_grad restatement (autograd through the oracle's denoiser)
