@@ -476,14 +476,13 @@ __global__ void __launch_bounds__(320, 1) wav_conv_tc2_kernel(const float* __res
 #pragma unroll
       for (int cil = 0; cil < CI_PER_CHUNK; ++cil) {
         const float2 st = __ldg(stb + c * CI_PER_CHUNK + cil);
-        const float sc = st.y, sh = -st.x * st.y;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int idx = lane + 32 * i;
           if (idx < WROW) {
             // Samples past the end of the row (loaded as 0) only meet the zero weight of the 16th tap or belong to
             // positions >= Lo, whose accumulator rows are never read: any finite value will do, no select needed.
-            const float v = fmaf(nx[cil][i], sc, sh);
+            const float v = (nx[cil][i] - st.x) * st.y;     // the reference's order: subtract the mean, then scale
             wraw[cil * WROW + idx] = fmaxf(v, 0.3f * v);
           }
         }
