@@ -20,7 +20,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from livelyspeaker_b200 import (ClassifierFreeSampleModel, Decoder_TRANSFORMER, create_model_and_diffusion,  # noqa: E402
-                                load_model_wo_clip, synthetic)
+                                load_model_wo_clip, metrics, synthetic)
+from livelyspeaker_b200.ted_evaluator import EmbeddingSpaceEvaluator  # noqa: E402  (model.ted_evaluator in the reference)
 
 
 def generate_args():
@@ -77,6 +78,19 @@ def main():
     n = diffusion.num_timesteps - skip_steps
     print("%s: %d clips x %d steps in %.1f ms (%.0f clips/s), motions %s, finite=%s"
           % (a.mode, B, n, dt * 1e3, B / dt, tuple(aligned_motions.shape), bool(torch.isfinite(aligned_motions).all())))
+
+    # ---- the script's metrics on the sampler's output, still on the device (scripts/test_RAG_ted.py:35, 84-131)
+    torch.save({"pose_dim": 27, "gen_dict": synthetic.synth_embed_state_dict(seed=5)}, os.path.join(tmp, "autoencoder.bin"))
+    embed_space_evaluator = EmbeddingSpaceEvaluator(os.path.join(tmp, "autoencoder.bin"))
+    vec_seq = y['origin_x'].permute(0, 3, 1, 2).reshape(B, 34, -1)
+    embed_space_evaluator.push_samples(aligned_motions, vec_seq)
+    frechet_dist, feat_dist = embed_space_evaluator.get_scores()
+    _, beat_mask = metrics.motion_beats(sample)
+    onsets = [[0.2 * (k + 1) for k in range(10)] for _ in range(B)]  # librosa.onset.onset_detect(...) in the reference
+    s = metrics.beat_align_score(beat_mask, onsets)
+    print("metrics (synthetic weights, so the values mean nothing): FGD %.4f, feat_dist %.4f, diversity %.4f, beat_score %.4f,"
+          " motion_beats_sum %d" % (frechet_dist, feat_dist, embed_space_evaluator.get_diversity_scores(),
+                                    s["beat_align_score_sum"] / max(1, s["num_beats"]), s["motion_beats_sum"]))
 
 
 if __name__ == "__main__":
