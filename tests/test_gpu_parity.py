@@ -842,6 +842,15 @@ def test_fgd_features_and_scores_on_device(golden_fgd, tmp_path):
         o_mu, o_lv = evaluator_oracle.pose_features(sd, poses)
         np.testing.assert_allclose(mu.cpu().numpy(), o_mu.numpy(), rtol=RTOL, atol=ATOL)
         np.testing.assert_allclose(logvar.cpu().numpy(), o_lv.numpy(), rtol=RTOL, atol=ATOL)
+    # full evaluation batch (512 clips): every clip's features are independent of its neighbours in the CTA - bit-exact
+    big = 0.3 * torch.randn(512, 34, fc.POSE_DIM, generator=g).to(DEV)
+    _, mu_all, lv_all = ev.net(big)
+    perm = torch.randperm(512, generator=g).to(DEV)
+    _, mu_perm, _ = ev.net(big[perm])
+    assert torch.equal(mu_perm, mu_all[perm])
+    for b in (0, 255, 511):
+        _, mu_one, lv_one = ev.net(big[b:b + 1])
+        assert torch.equal(mu_one[0], mu_all[b]) and torch.equal(lv_one[0], lv_all[b])
     # variational encoding: one randn_like draw of the global (CUDA) generator, embedding_net.py:9-12
     poses = poses.to(DEV)
     torch.manual_seed(5)
