@@ -427,6 +427,8 @@ def main():
     def params_at(k0, n):                 # loop iterations k0 .. k0+n-1 (the loop counts i = n_loop-1 .. 0, wrapping)
         return [params_all[n_loop - 1 - ((k0 + j) % n_loop)] for j in range(n)]
 
+    draw_launches = [0]
+
     def run_chunk(k0, x_in, steady):
         """C consecutive loop iterations as p_sample_loop runs them on the fused route: the reference's per-step draws
         (full chunks after the first: ONE torch-compatible launch, or a CUDA-graph replay of the 3C torch kernels when
@@ -438,6 +440,8 @@ def main():
                 diffusion.graph_draws = False
         if graphed is not None:
             e_c, e_u, nz = graphed.draw()
+            if isinstance(graphed, gd._FusedDraws):
+                draw_launches[0] += 1         # ls_randn_torch_compat: one kernel of ours per chunk
         else:
             e_c = [torch.randn(B, 1, 512, device=dev) for _ in range(C)]
             e_u = [torch.randn(B, 1, 512, device=dev) for _ in range(C)]
@@ -476,7 +480,7 @@ def main():
     n_warm += 1
     K, W = n_timed * C, n_warm * C
     clocks.wait_first_sample()
-    launches0 = eng.launch_count()
+    launches0 = eng.launch_count() + draw_launches[0]
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_timed)]
     import gc
     gc.collect()
@@ -491,7 +495,7 @@ def main():
     sync_all()
     clocks.mark_end()
     gc.enable()
-    launches = eng.launch_count() - launches0
+    launches = eng.launch_count() + draw_launches[0] - launches0      # fused launches + the one-launch draws
     clk = clocks.stop()
     per_launch = [s.elapsed_time(e) for s, e in ev]
     t_ms = sum(per_launch)

@@ -805,6 +805,43 @@ def test_rhythm_metric_on_device(golden_metrics):
         metrics.motion_beats(out.cpu())
 
 
+def test_one_launch_draws_are_torchs_draws():
+    """ls_randn_torch_compat (the 48 draws of a fused chunk in one launch, stateless Philox4x32-10 + curand's Box-Muller)
+    equals torch.randn_like bit for bit - values and the generator's final state - for the sampler's tensors and for
+    sizes that exercise every tail of ATen's grid-stride mapping (1 element, below one block, several iterations per
+    thread), and the sampler actually uses it (no silent fall-back to the graph replay).  RAG.py:10-13,
+    gaussian_diffusion.py:543 are the draws it stands for."""
+    import ctypes
+    from livelyspeaker_b200 import _cabi
+    from livelyspeaker_b200.gaussian_diffusion import _FusedDraws
+    like = torch.empty(34, 512, 9, 3, device=DEV).permute(1, 2, 3, 0)
+    fd = _FusedDraws(16, 512, 512, like)
+    assert fd.ok and fd.n == 48
+    lib = _cabi.load_library()
+    gen = torch.cuda.default_generators[0]
+    for numels in ([1], [255, 256, 257], [1184 * 256 * 4 + 5, 3], [5_000_000, 7, 1184 * 256 * 8]):
+        outs = [torch.empty(n, device=DEV) for n in numels]
+        torch.manual_seed(1234 + len(numels))
+        torch.randn(17, device=DEV)                       # a non-zero starting offset
+        state = torch.cuda.get_rng_state(DEV)
+        want = [torch.randn_like(t) for t in outs]
+        end_torch = torch.cuda.get_rng_state(DEV)
+        torch.cuda.set_rng_state(state, DEV)
+        seed, off = gen.initial_seed(), gen.get_offset()
+        inc = ctypes.c_uint64(0)
+        rc = lib.ls_randn_torch_compat(len(outs), (ctypes.c_void_p * len(outs))(*[t.data_ptr() for t in outs]),
+                                       (ctypes.c_int64 * len(outs))(*numels), ctypes.c_uint64(seed), ctypes.c_uint64(off),
+                                       ctypes.byref(inc), 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        gen.set_offset(off + inc.value)
+        assert torch.equal(torch.cuda.get_rng_state(DEV), end_torch)
+        for a, b in zip(outs, want):
+            assert torch.equal(a, b)
+    rc = lib.ls_randn_torch_compat(1, (ctypes.c_void_p * 1)(outs[0].data_ptr()), (ctypes.c_int64 * 1)(4), ctypes.c_uint64(1),
+                                   ctypes.c_uint64(6), ctypes.byref(inc), 0, None)
+    assert rc != 0                                        # torch keeps the offset a multiple of 4; anything else is refused
+
+
 def test_fgd_features_and_scores_on_device(golden_fgd, tmp_path):
     """ls_pose_features (FGD features) against the fixture made by the reference's EmbeddingNet and
     EmbeddingSpaceEvaluator and against the oracle; ragged batches (the kernel packs 4 clips per CTA); the whole
