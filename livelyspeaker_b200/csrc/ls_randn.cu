@@ -43,7 +43,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // What curand_init(seed, subsequence = idx, offset) followed by the it-th curand_normal4 returns, without the generator
 // state: curand_init leaves the counter at (offset / 4, idx) - torch's offsets are multiples of 4 - and every curand4
 // call returns Philox(counter) and advances it by one.  Going through curandStatePhilox4_32_10_t costs two Philox
-// evaluations per draw (curand_init and curand4 each compute one ahead) plus the state traffic: 156 -> 50 us per chunk.
+// evaluations per draw (curand_init and curand4 each compute one ahead) plus the state traffic: 156 -> 101 us per chunk
+// (ncu).  What is left is torch's mapping itself: at these sizes a thread of ATen's grid uses 1 or 2 of the 4 values of its
+// Philox call, so 14 M Philox evaluations feed 16 M normals; a persistent grid walking the (tensor, block) pairs instead of
+// 57k short blocks was tried and is not faster (110 us): the kernel is bound by its integer instruction stream.
 // Only the Box-Muller pairs that land inside the tensor are evaluated (_curand_box_muller, curand_normal.h:70-90, the
 // function curand_normal4 is made of).
 __global__ void __launch_bounds__(RN_BLOCK) randn_torch_compat_kernel(const __grid_constant__ RandnJobs jobs,
