@@ -8,9 +8,10 @@ p_mean_variance (:284-399), p_sample (:507-558), p_sample_loop[_progressive]
 condition_mean / condition_score (:429-481), plms_sample[_loop] (:1016-1211),
 _extract_into_tensor (:1651-1664), ddim_reverse_sample (:857-893), and the *_with_grad samplers (:444-505, :560-606,
 :800-855) whose model call is differentiable with respect to x through a hand-written
-backward kernel (ls_cfg_forward_grad / ls_cfg_backward).  Training losses and VLB terms
-need gradients with respect to the weights: outside the hot path,
-they raise NotImplementedError.
+backward kernel (ls_cfg_forward_grad / ls_cfg_backward).  training_losses (:1249-1401, HUBER branch)
+evaluates FORWARD values on the device (no autograd graph: the backward pass with respect to
+the weights is not built); the VLB terms (_vb_terms_bpd, _prior_bpd, calc_bpd_loop) are outside
+the path and raise NotImplementedError.
 
 Two execution routes:
   * fused  - the model is this package's ClassifierFreeSampleModel(RAG) and no Python
@@ -777,8 +778,7 @@ class GaussianDiffusion:
 
     # ------------------------------------------------------------------ out of scope
     def _out_of_scope(self, *a, **k):
-        raise NotImplementedError("training / VLB / *_with_grad are outside the sampling hot path "
-                                  "(SURVEY.md section 8f)")
+        raise NotImplementedError("the VLB terms are outside the sampling hot path (SURVEY.md sections 2 and 8f)")
 
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None, dataset=None):
         """gaussian_diffusion.py:1249-1401, LossType.HUBER (what model_util.py:61 configures) - FORWARD VALUES: q_sample,
