@@ -31,4 +31,16 @@ dec.load_state_dict(synthetic.synth_sag_state_dict(seed=3), strict=True)
 dec = dec.to(DEV).eval()
 o = dec({"x": x, "z": torch.randn(B, 512, device=DEV), "mask": torch.ones(B, 34, dtype=torch.bool, device=DEV)})["output"]
 print("sag", bool(torch.isfinite(o).all()))
+from livelyspeaker_b200 import embedding_net, metrics
+from livelyspeaker_b200.gaussian_diffusion import _FusedDraws
+net = embedding_net.EmbeddingNet(27, 34).eval()
+net.load_state_dict(synthetic.synth_embed_state_dict(seed=5))
+for b in (1, 5):
+    f, _, _ = net(0.3 * torch.randn(b, 34, 27, device=DEV))
+print("pose features", bool(torch.isfinite(f).all()))
+ad, mask = metrics.motion_beats(out)
+print("motion beats", int(mask.sum()))
+fd = _FusedDraws(16, B, 512, torch.empty(34, B, 9, 3, device=DEV).permute(1, 2, 3, 0))
+fd.draw()
+print("one-launch draws verified against torch:", fd.ok)
 torch.cuda.synchronize()
