@@ -292,6 +292,16 @@ int ls_huber_terms(int64_t rows, int32_t n_frames, const float* target, const fl
                    int64_t n_z, const float* z_mu, const float* z_logvar, float* terms,
                    int32_t device, void* stream);
 
+/* Variational-bound terms of GaussianDiffusion._vb_terms_bpd / _prior_bpd (scripts/diffusion/gaussian_diffusion.py:1213-1247,
+ * 1573-1590; normal_kl and discretized_gaussian_log_likelihood of scripts/diffusion/losses.py:12-77).  All tensors dense
+ * [B][n] fp32 on the device, logvar1 / logvar2 one value per clip (LivelySpeaker's variances are fixed).  out[b] (device) =
+ * mean_i normal_kl(mean1, logvar1, mean2, logvar2) / ln 2, or - where t is given and t[b] == 0 - the mean discretised
+ * Gaussian negative log-likelihood of x_start under N(mean2, exp(logvar2)) / ln 2.  mean2 == NULL means 0 and logvar2 ==
+ * NULL means 0 (the prior term; then t must be NULL).  Stateless; errors through ls_last_error(NULL).                   */
+int ls_vb_terms(int32_t B, int64_t n, const float* x_start, const float* mean1, const float* mean2,
+                const float* logvar1, const float* logvar2, const int64_t* t, float* out, int32_t device,
+                void* stream);
+
 /* ---- latent features of the evaluation's pose autoencoder (FGD features) ----------------
  * scripts/model/embedding_net.py:40-79 (PoseEncoderConv.forward in eval mode) as called by
  * scripts/model/ted_evaluator.py:35-41 (EmbeddingSpaceEvaluator.push_samples).  All pointers are DEVICE fp32.

@@ -21,7 +21,7 @@ EXPORTS = ["ls_abi_version", "ls_last_error", "ls_create", "ls_destroy", "ls_loa
            "ls_finalize_weights", "ls_set_impl", "ls_get_impl", "ls_precompute_cond", "ls_wav_encoder",
            "ls_model_forward", "ls_model_forward_train", "ls_huber_terms", "ls_cfg_forward", "ls_cfg_forward_grad", "ls_cfg_backward", "ls_step", "ls_step_multi", "ls_sag_decode", "ls_sag_create", "ls_sag_decode_tc",
            "ls_sag_launch_count", "ls_sag_destroy", "ls_randn_torch_compat", "ls_q_sample", "ls_launch_count",
-           "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align", "ls_pose_features"]
+           "ls_debug_buffer", "ls_debug_hidden", "ls_motion_beats", "ls_beat_align", "ls_pose_features", "ls_vb_terms"]
 
 
 class LsConfig(ctypes.Structure):
@@ -437,3 +437,29 @@ def huber_terms(target, output, z_mu, z_logvar, terms):
                                 c_void_p(terms.data_ptr()), target.device.index or 0, _stream())
     if rc != 0:
         raise LsError("libls_b200 error %d: %s" % (rc, lib.ls_last_error(None).decode()))
+
+
+def vb_terms(x_start, mean1, mean2, logvar1, logvar2, t):
+    """ls_vb_terms: per-clip variational-bound term in bits.  x_start / mean1 / mean2 [B, ...] (mean2 None = 0),
+    logvar1 / logvar2 [B] (logvar2 None = 0), t [B] int64 or None (None: always the KL)."""
+    if mean1.device.type != "cuda":
+        raise LsError("the variational-bound terms run on a CUDA sm_100 device only (no CPU path)")
+    lib = load_library()
+    lib.ls_vb_terms.argtypes = [c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_int32, c_void_p]
+    B = mean1.shape[0]
+    dev = mean1.device
+
+    def dense(v, dtype=torch.float32):
+        return None if v is None else v.detach().to(device=dev, dtype=dtype).contiguous()
+
+    xs, m1, m2 = dense(x_start), dense(mean1), dense(mean2)
+    lv1, lv2, tt = dense(logvar1), dense(logvar2), dense(t, torch.int64)
+    out = torch.empty(B, dtype=torch.float32, device=dev)
+    ptr = lambda v: None if v is None else c_void_p(v.data_ptr())      # noqa: E731
+    with torch.cuda.device(dev):
+        rc = lib.ls_vb_terms(B, m1.numel() // B, ptr(xs), ptr(m1), ptr(m2), ptr(lv1), ptr(lv2), ptr(tt), ptr(out),
+                             dev.index or 0, _stream())
+    if rc != 0:
+        raise LsError("libls_b200 error %d: %s" % (rc, lib.ls_last_error(None).decode()))
+    return out

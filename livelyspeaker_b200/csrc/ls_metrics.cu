@@ -216,3 +216,74 @@ extern "C" int ls_huber_terms(int64_t rows, int32_t n_frames, const float* targe
   if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_huber_terms: %s", cudaGetErrorString(e));
   return LS_OK;
 }
+
+
+// ---- variational-bound terms (GaussianDiffusion._vb_terms_bpd / _prior_bpd / calc_bpd_loop) --------------------------
+// scripts/diffusion/gaussian_diffusion.py:1213-1247, 1573-1590 and scripts/diffusion/losses.py:12-77: per clip the mean
+// over all elements of normal_kl(true posterior || model) or, at t == 0, of the discretised Gaussian negative
+// log-likelihood of x_start, in bits.  With LivelySpeaker's fixed variances both log-variances are one number per clip.
+// fp32 element arithmetic in the reference's operation order (no contraction), one block per clip, fixed-order fp64 sum.
+namespace {
+__device__ __forceinline__ float approx_normal_cdf(float x) {                  // losses.py:46-51
+  const float x3 = __fmul_rn(__fmul_rn(x, x), x);                               // torch.pow(x, 3)
+  const float inner = __fmul_rn(0.7978845608028654f, __fadd_rn(x, __fmul_rn(0.044715f, x3)));
+  return __fmul_rn(0.5f, __fadd_rn(1.0f, tanhf(inner)));
+}
+__global__ void __launch_bounds__(256) vb_terms_kernel(long long n, const float* __restrict__ x_start,
+                                                       const float* __restrict__ mean1, const float* __restrict__ mean2,
+                                                       const float* __restrict__ logvar1, const float* __restrict__ logvar2,
+                                                       const long long* __restrict__ t, float* __restrict__ out) {
+  __shared__ double red[8];
+  const int b = blockIdx.x;
+  const float lv1 = logvar1[b], lv2 = logvar2 ? logvar2[b] : 0.f;
+  const bool nll = t != nullptr && t[b] == 0;
+  const float* xs = x_start + (size_t)b * n;
+  const float* m1 = mean1 + (size_t)b * n;
+  const float* m2 = mean2 ? mean2 + (size_t)b * n : nullptr;
+  // normal_kl (losses.py:12-43): 0.5 * (-1 + lv2 - lv1 + exp(lv1 - lv2) + (m1 - m2)^2 * exp(-lv2))
+  const float head = __fadd_rn(__fadd_rn(__fadd_rn(-1.0f, lv2), -lv1), expf(__fadd_rn(lv1, -lv2)));
+  const float inv_var2 = expf(-lv2);
+  const float inv_stdv = expf(-__fmul_rn(0.5f, lv2));                           // exp(-log_scales), log_scales = 0.5 * lv2
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const float mm = m2 ? m2[i] : 0.f;
+    float v;
+    if (!nll) {
+      const float d = __fadd_rn(m1[i], -mm);
+      v = __fmul_rn(0.5f, __fadd_rn(head, __fmul_rn(__fmul_rn(d, d), inv_var2)));
+    } else {                                                                    // losses.py:54-77, negated
+      const float x = xs[i], c = __fadd_rn(x, -mm);
+      const float cdf_plus = approx_normal_cdf(__fmul_rn(inv_stdv, __fadd_rn(c, 1.0f / 255.0f)));
+      const float cdf_min = approx_normal_cdf(__fmul_rn(inv_stdv, __fadd_rn(c, -(1.0f / 255.0f))));
+      float lp;
+      if (x < -0.999f) lp = logf(fmaxf(cdf_plus, 1e-12f));
+      else if (x > 0.999f) lp = logf(fmaxf(__fadd_rn(1.0f, -cdf_min), 1e-12f));
+      else lp = logf(fmaxf(__fadd_rn(cdf_plus, -cdf_min), 1e-12f));
+      v = -lp;
+    }
+    s += (double)v;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < 8; ++w) tot += red[w];
+    out[b] = (float)(tot / (double)n) / 0.6931471805599453f;                    // mean_flat(.) / np.log(2.0)
+  }
+}
+}  // namespace
+
+extern "C" int ls_vb_terms(int32_t B, int64_t n, const float* x_start, const float* mean1, const float* mean2,
+                           const float* logvar1, const float* logvar2, const int64_t* t, float* out, int32_t device,
+                           void* stream) {
+  if (B < 1 || n < 1 || !mean1 || !logvar1 || !out || (t != nullptr && (!x_start || !mean2 || !logvar2)))
+    return ls_fail(nullptr, LS_EINVAL, "ls_vb_terms: bad argument");
+  if (cudaSetDevice(device) != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_vb_terms: cudaSetDevice(%d)", device);
+  vb_terms_kernel<<<B, 256, 0, (cudaStream_t)stream>>>((long long)n, x_start, mean1, mean2, logvar1, logvar2,
+                                                        (const long long*)t, out);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_vb_terms: %s", cudaGetErrorString(e));
+  return LS_OK;
+}

@@ -10,8 +10,8 @@ _extract_into_tensor (:1651-1664), ddim_reverse_sample (:857-893), and the *_wit
 :800-855) whose model call is differentiable with respect to x through a hand-written
 backward kernel (ls_cfg_forward_grad / ls_cfg_backward).  training_losses (:1249-1401, HUBER branch)
 evaluates FORWARD values on the device (no autograd graph: the backward pass with respect to
-the weights is not built); the VLB terms (_vb_terms_bpd, _prior_bpd, calc_bpd_loop) are outside
-the path and raise NotImplementedError.
+the weights is not built); the variational-bound diagnostics (_vb_terms_bpd :1213-1247, _prior_bpd
+:1573-1590, calc_bpd_loop :1592-1645) run their element arithmetic in ls_vb_terms.
 
 Two execution routes:
   * fused  - the model is this package's ClassifierFreeSampleModel(RAG) and no Python
@@ -776,16 +776,13 @@ class GaussianDiffusion:
                 old_out = out
                 img = out["sample"]
 
-    # ------------------------------------------------------------------ out of scope
-    def _out_of_scope(self, *a, **k):
-        raise NotImplementedError("the VLB terms are outside the sampling hot path (SURVEY.md sections 2 and 8f)")
-
     def training_losses(self, model, x_start, t, model_kwargs=None, noise=None, dataset=None):
         """gaussian_diffusion.py:1249-1401, LossType.HUBER (what model_util.py:61 configures) - FORWARD VALUES: q_sample,
         the model in whatever mode it is in (training mode = per-clip condition dropout, ls_model_forward_train), and
         the loss terms reduced on the device by ls_huber_terms.  The returned tensors carry no autograd graph: the
         backward pass with respect to the weights (train_loop.py:146-186) is not built."""
         if self.loss_type != LossType.HUBER:
+            # the reference's KL branches cannot return either (their `pred` dict reads an undefined `target`, :1399-1401)
             raise NotImplementedError("only LossType.HUBER (model_util.py:61) is built: %s" % self.loss_type)
         if self.model_mean_type != ModelMeanType.START_X or self.model_var_type not in (ModelVarType.FIXED_SMALL,
                                                                                          ModelVarType.FIXED_LARGE):
@@ -829,4 +826,50 @@ class GaussianDiffusion:
         alpha_bar_next = _extract_into_tensor(self.alphas_cumprod_next, t, x.shape)
         mean_pred = out["pred_xstart"] * th.sqrt(alpha_bar_next) + th.sqrt(1 - alpha_bar_next) * eps
         return {"sample": mean_pred, "pred_xstart": out["pred_xstart"]}
-    calc_bpd_loop = _vb_terms_bpd = _prior_bpd = _out_of_scope
+
+    # ------------------------------------------------------------------ variational bound (diagnostics)
+    def _vb_terms_bpd(self, model, x_start, x_t, t, clip_denoised=True, model_kwargs=None):
+        """One term of the variational bound in bits per dimension (gaussian_diffusion.py:1213-1247): KL between the true
+        posterior q(x_{t-1} | x_t, x_0) and the model's, or - at t == 0 - the discretised decoder NLL.  The model call is
+        p_mean_variance (the fused kernel in mode 2); the element arithmetic and the per-clip means run in ls_vb_terms."""
+        from . import _cabi
+        true_mean, _, true_log_variance_clipped = self.q_posterior_mean_variance(x_start=x_start, x_t=x_t, t=t)
+        out = self.p_mean_variance(model, x_t, t, clip_denoised=clip_denoised, model_kwargs=model_kwargs)
+        B = x_start.shape[0]
+        first = (slice(None),) + (0,) * (x_start.dim() - 1)                # fixed variances: one value per clip
+        output = _cabi.vb_terms(x_start, true_mean, out["mean"], true_log_variance_clipped[first],
+                                out["log_variance"][first], t.reshape(B))
+        return {"output": output, "pred_xstart": out["pred_xstart"]}
+
+    def _prior_bpd(self, x_start):
+        """KL(q(x_T | x_0) || N(0, I)) in bits per dimension (gaussian_diffusion.py:1573-1590)."""
+        from . import _cabi
+        B = x_start.shape[0]
+        t = th.tensor([self.num_timesteps - 1] * B, device=x_start.device)
+        qt_mean, _, qt_log_variance = self.q_mean_variance(x_start, t)
+        first = (slice(None),) + (0,) * (x_start.dim() - 1)
+        return _cabi.vb_terms(None, qt_mean, None, qt_log_variance[first], None, None)
+
+    def calc_bpd_loop(self, model, x_start, clip_denoised=True, model_kwargs=None):
+        """The whole variational bound and the per-timestep x_0 / epsilon errors (gaussian_diffusion.py:1592-1645): for
+        t = T-1 .. 0 one randn_like draw, q_sample, _vb_terms_bpd; returns total_bpd, prior_bpd, vb / xstart_mse / mse
+        [N, T]."""
+        device = x_start.device
+        B = x_start.shape[0]
+        vb, xstart_mse, mse = [], [], []
+        flat = tuple(range(1, x_start.dim()))
+        for t in list(range(self.num_timesteps))[::-1]:
+            t_batch = th.tensor([t] * B, device=device)
+            noise = self.noise_source.randn_like(x_start)
+            x_t = self.q_sample(x_start=x_start, t=t_batch, noise=noise)
+            with th.no_grad():
+                out = self._vb_terms_bpd(model, x_start=x_start, x_t=x_t, t=t_batch, clip_denoised=clip_denoised,
+                                         model_kwargs=model_kwargs)
+            vb.append(out["output"])
+            xstart_mse.append(((out["pred_xstart"] - x_start) ** 2).mean(dim=flat))
+            eps = self._predict_eps_from_xstart(x_t, t_batch, out["pred_xstart"])
+            mse.append(((eps - noise) ** 2).mean(dim=flat))
+        vb, xstart_mse, mse = th.stack(vb, dim=1), th.stack(xstart_mse, dim=1), th.stack(mse, dim=1)
+        prior_bpd = self._prior_bpd(x_start)
+        total_bpd = vb.sum(dim=1) + prior_bpd
+        return {"total_bpd": total_bpd, "prior_bpd": prior_bpd, "vb": vb, "xstart_mse": xstart_mse, "mse": mse}

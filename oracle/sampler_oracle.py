@@ -192,6 +192,73 @@ def ddim_reverse_step(sd, tab, tmap, x, i, y, tape, nj, nf, clip_denoised=False)
     return x0 * torch.sqrt(ab_next) + torch.sqrt(1 - ab_next) * eps, x0
 
 
+def normal_kl(mean1, logvar1, mean2, logvar2):
+    """scripts/diffusion/losses.py:12-43 (tensor arguments)."""
+    return 0.5 * (-1.0 + logvar2 - logvar1 + torch.exp(logvar1 - logvar2) + ((mean1 - mean2) ** 2) * torch.exp(-logvar2))
+
+
+def _approx_cdf(x):
+    """losses.py:46-51."""
+    return 0.5 * (1.0 + torch.tanh(np.sqrt(2.0 / np.pi) * (x + 0.044715 * torch.pow(x, 3))))
+
+
+def discretized_gaussian_log_likelihood(x, means, log_scales):
+    """losses.py:54-77: log-probability of the 1/255-wide bin around x (data assumed rescaled to [-1, 1])."""
+    centered = x - means
+    inv_stdv = torch.exp(-log_scales)
+    cdf_plus = _approx_cdf(inv_stdv * (centered + 1.0 / 255.0))
+    cdf_min = _approx_cdf(inv_stdv * (centered - 1.0 / 255.0))
+    log_cdf_plus = torch.log(cdf_plus.clamp(min=1e-12))
+    log_one_minus_cdf_min = torch.log((1.0 - cdf_min).clamp(min=1e-12))
+    mid = torch.log((cdf_plus - cdf_min).clamp(min=1e-12))
+    return torch.where(x < -0.999, log_cdf_plus, torch.where(x > 0.999, log_one_minus_cdf_min, mid))
+
+
+def _mean_flat(v):
+    return v.mean(dim=list(range(1, v.dim())))
+
+
+def vb_terms_bpd(sd, tab, tmap, x_start, x_t, i, y, tape, nj, nf, clip_denoised=True):
+    """_vb_terms_bpd (gaussian_diffusion.py:1213-1247) at the batch-uniform spaced index i, fixed small variance.
+    One model call (two style draws).  Returns (output [N] in bits, pred_xstart)."""
+    c1, c2 = _pick(tab["posterior_mean_coef1"], i), _pick(tab["posterior_mean_coef2"], i)
+    log_var = _pick(tab["posterior_log_variance_clipped"], i) * torch.ones_like(x_start)
+    true_mean = c1 * x_start + c2 * x_t
+    x0 = _model_x0(sd, tab, tmap, x_t, i, y, tape, nj, nf, clip_denoised)
+    mean = c1 * x0 + c2 * x_t
+    if i == 0:
+        out = _mean_flat(-discretized_gaussian_log_likelihood(x_start, mean, 0.5 * log_var)) / np.log(2.0)
+    else:
+        out = _mean_flat(normal_kl(true_mean, log_var, mean, log_var)) / np.log(2.0)
+    return out, x0
+
+
+def prior_bpd(tab, x_start):
+    """_prior_bpd (:1573-1590): KL(q(x_T | x_0) || N(0, I)) in bits per dimension."""
+    T = len(tab["betas"])
+    qt_mean = _pick(tab["sqrt_alphas_cumprod"], T - 1) * x_start
+    qt_log_var = _pick(tab["log_one_minus_alphas_cumprod"], T - 1) * torch.ones_like(x_start)
+    zero = torch.zeros(())
+    return _mean_flat(normal_kl(qt_mean, qt_log_var, zero, zero)) / np.log(2.0)
+
+
+def calc_bpd_loop(sd, tab, tmap, x_start, y, tape, nj, nf, clip_denoised=True):
+    """calc_bpd_loop (:1592-1645): per step one randn_like draw, then the model's two style draws."""
+    T = len(tab["betas"])
+    vb, xstart_mse, mse = [], [], []
+    for i in range(T - 1, -1, -1):
+        noise = tape.draw_like(x_start)
+        x_t = q_sample(tab, x_start, i, noise)
+        out, x0 = vb_terms_bpd(sd, tab, tmap, x_start, x_t, i, y, tape, nj, nf, clip_denoised)
+        vb.append(out)
+        xstart_mse.append(_mean_flat((x0 - x_start) ** 2))
+        eps = (_pick(tab["sqrt_recip_alphas_cumprod"], i) * x_t - x0) / _pick(tab["sqrt_recipm1_alphas_cumprod"], i)
+        mse.append(_mean_flat((eps - noise) ** 2))
+    vb, xstart_mse, mse = torch.stack(vb, dim=1), torch.stack(xstart_mse, dim=1), torch.stack(mse, dim=1)
+    prior = prior_bpd(tab, x_start)
+    return {"total_bpd": vb.sum(dim=1) + prior, "prior_bpd": prior, "vb": vb, "xstart_mse": xstart_mse, "mse": mse}
+
+
 def training_losses(sd, tab, tmap, x_start, t_idx, y, noise, style_eps, cond_drop, nj, nf, lambda_vel=1.0):
     """GaussianDiffusion.training_losses, LossType.HUBER (gaussian_diffusion.py:1249-1401): q_sample at the per-clip
     spaced indices t_idx, RAG.forward in training mode (cond_drop = the Bernoulli mask of mask_cond, RAG.py:84-93;

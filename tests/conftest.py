@@ -71,6 +71,12 @@ def golden_train():
 
 
 @pytest.fixture(scope="session")
+def golden_vlb():
+    return {"ted": dict(np.load(os.path.join(GOLDEN, "vlb_ted.npz"))),
+            "beat": dict(np.load(os.path.join(GOLDEN, "vlb_beat.npz")))}
+
+
+@pytest.fixture(scope="session")
 def golden_fgd():
     return dict(np.load(os.path.join(GOLDEN, "fgd.npz")))
 

@@ -805,6 +805,82 @@ def test_rhythm_metric_on_device(golden_metrics):
         metrics.motion_beats(out.cpu())
 
 
+def _vlb_setup(name):
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import vlb_cases as vc
+    dims, sd, cfg, diffusion = build(name, vc.SPEC)
+    tab, tmap = schedule_oracle.build("cosine", 1000, vc.SPEC)
+    shape = (vc.B, dims.njoints, dims.nfeats, 34)
+    return vc, dims, sd, cfg, diffusion, tab, tmap, shape
+
+
+@pytest.mark.parametrize("name", ["ted", "beat"])
+def test_variational_bound_terms_vs_reference_fixture(name, golden_vlb):
+    """_vb_terms_bpd / _prior_bpd (gaussian_diffusion.py:1213-1247, 1573-1590): model call on the fused kernel (mode 2),
+    element arithmetic in ls_vb_terms, against the reference's outputs and the oracle on the recorded draws - KL terms
+    at several timesteps, the decoder NLL saturated and within a few sigma of the mean (all three branches of the
+    discretised likelihood), per-clip timesteps in one call."""
+    vc, dims, sd, cfg, diffusion, tab, tmap, shape = _vlb_setup(name)
+    g = golden_vlb[name]
+    y = synthetic.synth_cond(dims, vc.B, device=DEV)
+    y_cpu = synthetic.synth_cond(dims, vc.B)
+    for tag, (i, seed, clip, near) in vc.TERMS.items():
+        x_start, x_t, _ = vc.term_inputs(sampler_oracle.q_sample, tab, shape, i, seed)
+        if near:
+            x_start = torch.from_numpy(g["x_start_" + tag])
+        tape = sampler_oracle.NoiseTape(seed=seed)
+        with torch.no_grad():
+            want, want_x0 = sampler_oracle.vb_terms_bpd(sd, tab, tmap, x_start, x_t, i, y_cpu, tape, dims.njoints,
+                                                        dims.nfeats, clip_denoised=clip)
+        diffusion.noise_source = cfg.noise_source = ls.ReplayNoise(tape.record)
+        got = diffusion._vb_terms_bpd(cfg, x_start.to(DEV), x_t.to(DEV), torch.full((vc.B,), i, device=DEV),
+                                      clip_denoised=clip, model_kwargs={"y": y})
+        assert diffusion.noise_source.pos == 2 and set(got) == {"output", "pred_xstart"}
+        # near the mean the bin probability moves with (x_start - mean) / sigma, sigma = 0.03: the denoiser's own
+        # tolerance (1e-4 absolute on the mean) is 3e-3 of a sigma
+        rtol = 5e-3 if near else RTOL
+        _close(got["output"], g["vb_" + tag], rtol=rtol)
+        _close(got["output"], want, rtol=rtol)
+        _close(got["pred_xstart"], want_x0)
+        if "pred_" + tag in g:
+            _close(got["pred_xstart"], g["pred_" + tag])
+        print("%s %s: vb %s (reference %s)" % (name, tag, got["output"].tolist(), g["vb_" + tag].tolist()))
+    tag, ts, seed, clip = vc.MIXED
+    x_start, x_t = vc.mixed_inputs(sampler_oracle.q_sample, tab, shape)
+    torch.manual_seed(seed)
+    rec = [torch.randn(vc.B, 1, 512), torch.randn(vc.B, 1, 512)]
+    diffusion.noise_source = cfg.noise_source = ls.ReplayNoise(rec)
+    got = diffusion._vb_terms_bpd(cfg, x_start.to(DEV), x_t.to(DEV), torch.tensor(ts, device=DEV), clip_denoised=clip,
+                                  model_kwargs={"y": y})
+    _close(got["output"], g["vb_" + tag])
+    x_start = vc.loop_input(shape)
+    _close(diffusion._prior_bpd(x_start.to(DEV)), g["prior"], rtol=1e-5, atol=1e-8)
+    with pytest.raises(ls.LsError):
+        diffusion._prior_bpd(x_start)                    # host tensors: no CPU path
+
+
+def test_calc_bpd_loop_vs_reference_fixture(golden_vlb):
+    """calc_bpd_loop (gaussian_diffusion.py:1592-1645) over the 20-step respacing, TED: per step one randn_like draw and
+    the model's two style draws, in the reference's order."""
+    vc, dims, sd, cfg, diffusion, tab, tmap, shape = _vlb_setup("ted")
+    g = golden_vlb["ted"]
+    x_start = vc.loop_input(shape)
+    tape = sampler_oracle.NoiseTape(seed=vc.LOOP_SEED)
+    with torch.no_grad():
+        want = sampler_oracle.calc_bpd_loop(sd, tab, tmap, x_start, synthetic.synth_cond(dims, vc.B), tape, dims.njoints,
+                                            dims.nfeats, clip_denoised=True)
+    diffusion.noise_source = cfg.noise_source = ls.ReplayNoise(tape.record)
+    got = diffusion.calc_bpd_loop(cfg, x_start.to(DEV), clip_denoised=True,
+                                  model_kwargs={"y": synthetic.synth_cond(dims, vc.B, device=DEV)})
+    assert diffusion.noise_source.pos == len(tape.record) == 60
+    assert set(got) == {"total_bpd", "prior_bpd", "vb", "xstart_mse", "mse"} and tuple(got["vb"].shape) == (vc.B, 20)
+    for k in got:
+        _close(got[k], g["loop_" + k])
+        _close(got[k], want[k])
+
+
 def test_one_launch_draws_are_torchs_draws():
     """ls_randn_torch_compat (the 48 draws of a fused chunk in one launch, stateless Philox4x32-10 + curand's Box-Muller)
     equals torch.randn_like bit for bit - values and the generator's final state - for the sampler's tensors and for

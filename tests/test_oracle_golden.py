@@ -260,6 +260,43 @@ def test_rhythm_metric_oracle(golden_metrics):
     assert float(g["sigma"]) == metrics.SIGMA
 
 
+def _vlb_cases():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import vlb_cases
+    return vlb_cases
+
+
+@pytest.mark.parametrize("tag", ["t19", "t1", "t0_near", "loop"])
+def test_oracle_variational_bound_vs_reference_fixture(tag, golden_vlb):
+    """The oracle's _vb_terms_bpd / _prior_bpd / calc_bpd_loop restatement against the reference's outputs
+    (tests/golden/make_golden_vlb.py), TED: KL terms, the discretised decoder NLL away from its clamp, the whole loop."""
+    vc = _vlb_cases()
+    g = golden_vlb["ted"]
+    dims = synthetic.TED
+    sd = synthetic.synth_state_dict(dims, seed=1)
+    tab, tmap = schedule_oracle.build("cosine", 1000, vc.SPEC)
+    shape = (vc.B, dims.njoints, dims.nfeats, 34)
+    y = synthetic.synth_cond(dims, vc.B)
+    with torch.no_grad():
+        if tag == "loop":
+            x_start = vc.loop_input(shape)
+            o = sampler_oracle.calc_bpd_loop(sd, tab, tmap, x_start, y, sampler_oracle.NoiseTape(seed=vc.LOOP_SEED),
+                                             dims.njoints, dims.nfeats, clip_denoised=True)
+            for k in ("total_bpd", "prior_bpd", "vb", "xstart_mse", "mse"):
+                np.testing.assert_allclose(o[k].numpy(), g["loop_" + k], rtol=2e-5, atol=1e-6)
+            np.testing.assert_allclose(sampler_oracle.prior_bpd(tab, x_start).numpy(), g["prior"], rtol=1e-5, atol=1e-8)
+            return
+        i, seed, clip, near = vc.TERMS[tag]
+        x_start, x_t, _ = vc.term_inputs(sampler_oracle.q_sample, tab, shape, i, seed)
+        if near:
+            x_start = torch.from_numpy(g["x_start_" + tag])
+        o, _ = sampler_oracle.vb_terms_bpd(sd, tab, tmap, x_start, x_t, i, y, sampler_oracle.NoiseTape(seed=seed),
+                                           dims.njoints, dims.nfeats, clip_denoised=clip)
+    np.testing.assert_allclose(o.numpy(), g["vb_" + tag], rtol=2e-5, atol=1e-6)
+
+
 def _fgd_cases():
     import os
     import sys
