@@ -26,26 +26,23 @@ def _sqrtm(m):
 
 class EmbeddingSpaceEvaluator:
     def __init__(self, embed_net_path="/p300/wangchy/zhiyh/ted_output/gesture_autoencoder_checkpoint_best.bin"):
-        ckpt = torch.load(embed_net_path, map_location="cpu")
-        n_frames = 34
-        self.pose_dim = ckpt['pose_dim']
-        self.net = EmbeddingNet(self.pose_dim, n_frames)
-        self.net.load_state_dict(ckpt['gen_dict'])
-        self.net.train(False)
-        self.net.freeze_pose_nets()
+        checkpoint = torch.load(embed_net_path, map_location="cpu")     # {'pose_dim': int, 'gen_dict': state_dict}
+        self.pose_dim = int(checkpoint["pose_dim"])
+        net = EmbeddingNet(self.pose_dim, 34)                            # 34-frame clips (:17)
+        net.load_state_dict(checkpoint["gen_dict"])                      # strict: encoder AND decoder keys
+        net.eval()
+        net.freeze_pose_nets()
+        self.net = net
         self.reset()
 
     def reset(self):
-        self.real_feat_list = []
-        self.generated_feat_list = []
-        self.recon_err_diff = []
+        self.real_feat_list, self.generated_feat_list, self.recon_err_diff = [], [], []
 
     def push_samples(self, generated_poses, real_poses):
         """Both [B, 34, pose_dim] on a CUDA device (:35-41)."""
-        real_feat, _, _ = self.net(real_poses, variational_encoding=False)
-        generated_feat, _, _ = self.net(generated_poses, variational_encoding=False)
-        self.real_feat_list.append(real_feat.cpu().numpy())
-        self.generated_feat_list.append(generated_feat.cpu().numpy())
+        for poses, keep in ((real_poses, self.real_feat_list), (generated_poses, self.generated_feat_list)):
+            feat = self.net(poses, variational_encoding=False)[0]        # the mu head (ls_pose_features)
+            keep.append(feat.cpu().numpy())
 
     def get_features_for_viz(self):
         import umap                      # optional dependency of the reference (:48-57); not needed for the scores
@@ -75,21 +72,22 @@ class EmbeddingSpaceEvaluator:
         sigma1, sigma2 = np.atleast_2d(sigma1), np.atleast_2d(sigma2)
         assert mu1.shape == mu2.shape, 'Training and test mean vectors have different lengths'
         assert sigma1.shape == sigma2.shape, 'Training and test covariances have different dimensions'
-        covmean = _sqrtm(sigma1.dot(sigma2))
-        if not np.isfinite(covmean).all():
+        root = _sqrtm(sigma1 @ sigma2)
+        if not np.all(np.isfinite(root)):          # nearly singular product: regularise both covariances
             print('fid calculation produces singular product; adding %s to diagonal of cov estimates' % eps)
-            offset = np.eye(sigma1.shape[0]) * eps
-            covmean = _sqrtm((sigma1 + offset).dot(sigma2 + offset))
-        if np.iscomplexobj(covmean):
-            if not np.allclose(np.diagonal(covmean).imag, 0, atol=1e-3):
-                raise ValueError('Imaginary component {}'.format(np.max(np.abs(covmean.imag))))
-            covmean = covmean.real
-        diff = mu1 - mu2
-        return diff.dot(diff) + np.trace(sigma1) + np.trace(sigma2) - 2 * np.trace(covmean)
+            jitter = eps * np.eye(len(sigma1))
+            root = _sqrtm((sigma1 + jitter) @ (sigma2 + jitter))
+        if np.iscomplexobj(root):                  # numerical noise may leave a small imaginary part
+            if not np.allclose(np.diagonal(root).imag, 0, atol=1e-3):
+                raise ValueError('Imaginary component {}'.format(np.max(np.abs(root.imag))))
+            root = np.real(root)
+        d = mu1 - mu2
+        return float(d @ d) + np.trace(sigma1) + np.trace(sigma2) - 2.0 * np.trace(root)
 
     def get_diversity_scores(self):
         """Mean L1 distance between the first 500 pushed feature batches and 500 randomly drawn ones (:147-154)."""
-        feat1 = np.vstack(self.generated_feat_list[:500])
-        random_idx = torch.randperm(len(self.generated_feat_list))[:500]
-        feat2 = np.vstack([self.generated_feat_list[x] for x in random_idx])
-        return np.mean(np.sum(np.absolute(feat1 - feat2), axis=-1))
+        batches = self.generated_feat_list
+        head = np.vstack(batches[:500])
+        order = torch.randperm(len(batches))[:500]               # the one draw of the global generator (:149)
+        shuffled = np.vstack([batches[int(k)] for k in order])
+        return np.abs(head - shuffled).sum(axis=-1).mean()
