@@ -21,7 +21,7 @@ constexpr int RN_BLOCK = 256, RN_UNROLL = 4, RN_MAX = LS_RANDN_MAX_TENSORS;
 struct RandnJob {
   float* out;
   unsigned long long offset;
-  unsigned int numel, grid;
+  unsigned int numel, grid, iters;     // iters = Philox calls per thread of torch's grid: (numel - 1) / (256 * grid * 4) + 1
 };
 struct RandnJobs {
   RandnJob j[RN_MAX];
@@ -44,7 +44,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 // state: curand_init leaves the counter at (offset / 4, idx) - torch's offsets are multiples of 4 - and every curand4
 // call returns Philox(counter) and advances it by one.  Going through curandStatePhilox4_32_10_t costs two Philox
 // evaluations per draw (curand_init and curand4 each compute one ahead) plus the state traffic: 156 -> 101 us per chunk
-// (ncu).  What is left is torch's mapping itself: at these sizes a thread of ATen's grid uses 1 or 2 of the 4 values of its
+// (ncu), and 76 us with 32-bit index arithmetic and the trip count computed on the host.  What is left is torch's mapping itself: at these sizes a thread of ATen's grid uses 1 or 2 of the 4 values of its
 // Philox call, so 14 M Philox evaluations feed 16 M normals; a persistent grid walking the (tensor, block) pairs instead of
 // 57k short blocks was tried and is not faster (110 us): the kernel is bound by its integer instruction stream.
 // Only the Box-Muller pairs that land inside the tensor are evaluated (_curand_box_muller, curand_normal.h:70-90, the
@@ -53,23 +53,23 @@ __global__ void __launch_bounds__(RN_BLOCK) randn_torch_compat_kernel(const __gr
                                                                       unsigned long long seed) {
   const RandnJob& jb = jobs.j[blockIdx.y];
   if (blockIdx.x >= jb.grid) return;
-  const unsigned long long idx = (unsigned long long)blockIdx.x * RN_BLOCK + threadIdx.x;
-  const long long stride = (long long)RN_BLOCK * jb.grid, numel = jb.numel;
-  const long long rounded = ((numel - 1) / (stride * RN_UNROLL) + 1) * stride * RN_UNROLL;
+  // 32-bit index arithmetic (numel < 2^31, so every position below numel + 4 * stride fits in 32 bits) and the trip
+  // count from the host: a 64-bit division per thread cost as much as the Philox evaluation itself.
+  const unsigned int idx = blockIdx.x * RN_BLOCK + threadIdx.x, stride = RN_BLOCK * jb.grid, numel = jb.numel;
   const uint2 key = make_uint2((unsigned int)seed, (unsigned int)(seed >> 32));
   unsigned long long ctr = jb.offset >> 2;
   float* __restrict__ out = jb.out;
-  for (long long li = (long long)idx; li < rounded; li += stride * RN_UNROLL, ++ctr) {
-    if (li >= numel) continue;
-    const uint4 v = philox4x32_10(make_uint4((unsigned int)ctr, (unsigned int)(ctr >> 32), (unsigned int)idx,
-                                             (unsigned int)(idx >> 32)), key);
+  unsigned int li = idx;
+  for (unsigned int it = 0; it < jb.iters; ++it, ++ctr, li += 4u * stride) {
+    if (li >= numel) break;              // later iterations lie further out still
+    const uint4 v = philox4x32_10(make_uint4((unsigned int)ctr, (unsigned int)(ctr >> 32), idx, 0u), key);
     const float2 a = _curand_box_muller(v.x, v.y);
     out[li] = a.x;
     if (li + stride < numel) out[li + stride] = a.y;
-    if (li + 2 * stride < numel) {
+    if (li + 2u * stride < numel) {
       const float2 b = _curand_box_muller(v.z, v.w);
-      out[li + 2 * stride] = b.x;
-      if (li + 3 * stride < numel) out[li + 3 * stride] = b.y;
+      out[li + 2u * stride] = b.x;
+      if (li + 3u * stride < numel) out[li + 3u * stride] = b.y;
     }
   }
 }
@@ -96,11 +96,12 @@ extern "C" int ls_randn_torch_compat(int32_t n, float* const* outs, const int64_
     const unsigned long long numel = (unsigned long long)numels[i];
     unsigned int grid = (unsigned int)((numel + RN_BLOCK - 1) / RN_BLOCK);
     if (grid > grid_cap) grid = grid_cap;
-    jobs.j[i] = RandnJob{outs[i], off, (unsigned int)numel, grid};
-    off += ((numel - 1) / ((unsigned long long)RN_BLOCK * grid * RN_UNROLL) + 1) * 4ull;
+    const unsigned long long iters = (numel - 1) / ((unsigned long long)RN_BLOCK * grid * RN_UNROLL) + 1;
+    jobs.j[i] = RandnJob{outs[i], off, (unsigned int)numel, grid, (unsigned int)iters};
+    off += iters * 4ull;
     if (grid > max_grid) max_grid = grid;
   }
-  for (int i = n; i < RN_MAX; ++i) jobs.j[i] = RandnJob{nullptr, 0, 0, 0};
+  for (int i = n; i < RN_MAX; ++i) jobs.j[i] = RandnJob{nullptr, 0, 0, 0, 0};
   randn_torch_compat_kernel<<<dim3(max_grid, n), RN_BLOCK, 0, (cudaStream_t)stream>>>(jobs, seed);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ls_fail(nullptr, LS_ECUDA, "ls_randn_torch_compat: %s", cudaGetErrorString(e));

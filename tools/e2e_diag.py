@@ -5,18 +5,24 @@ import torch
 import livelyspeaker_b200 as ls
 from livelyspeaker_b200 import synthetic
 dev = torch.device("cuda:0")
-dims = synthetic.TED
+NAME = sys.argv[1] if len(sys.argv) > 1 else "ted"            # python tools/e2e_diag.py [ted|beat]
+dims = synthetic.dims_for(NAME)
 args = types.SimpleNamespace(mdm_condm='text', latent_dim=512, ff_size=1024, layers=8, cond_mask_prob=0.1, arch='trans_enc',
                              emb_trans_dec=False, dataset='humanml', lang_model=None, mlpact='silu', diffusion_steps=1000,
                              noise_schedule='cosine', sigma_small=True, lambda_vel=1.0, lambda_rcxyz=0.0, lambda_fc=0.0)
-B = 512
-model, diffusion = ls.create_model_and_diffusion(args, "")
+B = 512 if NAME == "ted" else 256
+if NAME == "ted":
+    model, diffusion = ls.create_model_and_diffusion(args, "")
+else:
+    from livelyspeaker_b200 import beat_model_util
+    args.njoints = 47
+    model, diffusion = beat_model_util.create_model_and_diffusion(args, "")
 model.load_state_dict(synthetic.synth_state_dict(dims, seed=1))
 cfg = ls.ClassifierFreeSampleModel(model).to(dev).eval()
 eng = model.engine(B)
 y_host = synthetic.synth_cond(dims, B, seed=233)
 y_pin = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in y_host.items()}
-shape = (B, 9, 3, 34)
+shape = (B, dims.njoints, dims.nfeats, 34)
 
 def once(n, chunk):
     diffusion.fused_chunk = chunk
@@ -39,6 +45,11 @@ for _ in range(3):
     eng.set_cond(y, force=True)
     torch.cuda.synchronize(); print("set_cond (WavEncoder + projections) %.2f ms" % ((time.perf_counter() - t0) * 1e3))
 
+if NAME != "ted":
+    from livelyspeaker_b200 import gaussian_diffusion as gd
+    perm_like = torch.empty(34, B, dims.njoints, dims.nfeats, device=dev).permute(1, 2, 3, 0)
+    print("chunk draws served by:", type(gd.chunk_draws(eng, 16, B, 512, perm_like)).__name__)
+    sys.exit(0)
 # SAG decoder (config 3 front end): time at B=256
 dec = ls.Decoder_TRANSFORMER(latent_dim=512, n_pre_poses=4, use_style=False)
 dec.load_state_dict(synthetic.synth_sag_state_dict(seed=3))
@@ -58,7 +69,7 @@ for Bs in (256, 512):
 
 # which source serves the draws of a full chunk on this box
 from livelyspeaker_b200 import gaussian_diffusion as gd
-perm_like = torch.empty(34, B, 9, 3, device=dev).permute(1, 2, 3, 0)
+perm_like = torch.empty(34, B, dims.njoints, dims.nfeats, device=dev).permute(1, 2, 3, 0)
 srcd = gd.chunk_draws(eng, 16, B, 512, perm_like)
 print("chunk draws served by:", type(srcd).__name__, "(fused kernel verified against torch: %s)"
       % eng.graphed_draws(16, B, 512, perm_like, gd._FusedDraws).ok)
