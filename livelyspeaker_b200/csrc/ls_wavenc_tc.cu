@@ -272,7 +272,7 @@ int lsw_audio_proj(ls_handle* h, const float* af_cm, int nb, float* A, cudaStrea
 // =====================================================================================================================
 namespace {
 
-constexpr int C1 = 32, C1_TILE = 256, C1_STRIDE = 5, C1_PAD = 1600;
+constexpr int C1 = 32, C1_TILE = 256, C1_POS = 4, C1_SPAN = C1_TILE * C1_POS, C1_STRIDE = 5, C1_PAD = 1600;
 
 // V values per lane in, lane idx holds the sum over the 32 lanes of value idx (V = 32: idx = lane)
 __device__ __forceinline__ void butterfly32(float* v, int lane) {
@@ -292,17 +292,16 @@ __device__ __forceinline__ void butterfly32(float* v, int lane) {
 // layer 1: audio [B][L0] -> raw accumulators [B][32][L1] + partials part[b][c][tile] = (sum, sum of squares).
 // The 480 weights travel as a kernel PARAMETER (constant bank): every FMA takes its weight as a constant operand.  With
 // the weights in shared memory the kernel issued one LDS per FMA and was LSU-bound at 266 us for 517 MB of output.
-// Now instruction-issue-bound (75 % issue-active, 223 us).  Tried: two positions per thread to pay the statistics'
-// butterflies once per thread - 148 registers halve the occupancy and the kernel gets slower (even at 128 registers).
+// Instruction-issue-bound (75 % issue-active at 223 us with one position per thread; see the loop below).
 struct Conv1W { float w[C1 * CONV_K]; };
-__global__ void __launch_bounds__(C1_TILE) wav_conv1_kernel(const float* __restrict__ audio, const __grid_constant__ Conv1W cw,
+__global__ void __launch_bounds__(C1_TILE, 2) wav_conv1_kernel(const float* __restrict__ audio, const __grid_constant__ Conv1W cw,
                                                             float* __restrict__ out, float2* __restrict__ part, int L0, int L1,
                                                             int n_tiles) {
-  constexpr int XW = (C1_TILE - 1) * C1_STRIDE + CONV_K;
+  constexpr int XW = (C1_SPAN - 1) * C1_STRIDE + CONV_K;
   __shared__ float xs[XW + 1];
   __shared__ float wpart[C1_TILE / 32][2 * C1];
   const int b = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int lo0 = tile * C1_TILE, lo = lo0 + tid;
+  const int lo0 = tile * C1_SPAN;
   const float* ab = audio + (size_t)b * L0;
   const int x0 = lo0 * C1_STRIDE - C1_PAD;
   for (int i = tid; i < XW; i += C1_TILE) {
@@ -310,22 +309,32 @@ __global__ void __launch_bounds__(C1_TILE) wav_conv1_kernel(const float* __restr
     xs[i] = (g >= 0 && g < L0) ? ab[g] : 0.f;
   }
   __syncthreads();
-  float x[CONV_K];
+  // A thread takes C1_POS positions (lo0 + tid + 256 p), one after the other, and keeps the running sum and sum of
+  // squares of its 32 channels: the two 32-value butterflies below are paid once per thread, not once per position
+  // (they were a fifth of the instruction stream): 224 -> 204 us.  Sequential on purpose (unroll 1) and capped at 128
+  // registers: unrolled, the compiler keeps every position's accumulators live; uncapped, it hoists the 480 weights
+  // out of the loop into 254 registers.  Two passes of 16 channels (one butterfly each, 64-80 registers) measured slower.
+  float acc[C1], sq[C1];
 #pragma unroll
-  for (int k = 0; k < CONV_K; ++k) x[k] = xs[tid * C1_STRIDE + k];
-  const bool valid = lo < L1;
-  float acc[C1];
+  for (int c = 0; c < C1; ++c) acc[c] = sq[c] = 0.f;
+#pragma unroll 1
+  for (int p = 0; p < C1_POS; ++p) {
+    const int lp = tid + C1_TILE * p, lo = lo0 + lp;
+    if (lo >= L1) break;
+    float x[CONV_K];
 #pragma unroll
-  for (int c = 0; c < C1; ++c) {
-    float a = 0.f;
+    for (int k = 0; k < CONV_K; ++k) x[k] = xs[lp * C1_STRIDE + k];
+    float* dst = out + (size_t)b * C1 * L1 + lo;
 #pragma unroll
-    for (int k = 0; k < CONV_K; ++k) a = fmaf(cw.w[c * CONV_K + k], x[k], a);
-    acc[c] = valid ? a : 0.f;
-    if (valid) out[((size_t)b * C1 + c) * L1 + lo] = a;
+    for (int c = 0; c < C1; ++c) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < CONV_K; ++k) a = fmaf(cw.w[c * CONV_K + k], x[k], a);
+      dst[(size_t)c * L1] = a;
+      acc[c] += a;
+      sq[c] = fmaf(a, a, sq[c]);
+    }
   }
-  float sq[C1];
-#pragma unroll
-  for (int c = 0; c < C1; ++c) sq[c] = acc[c] * acc[c];
   butterfly32(acc, lane);
   butterfly32(sq, lane);
   wpart[warp][lane] = acc[0];
@@ -748,7 +757,7 @@ int lsw_encoder_fused(ls_handle* h, const float* audio, const float* /*w0: uploa
                       int nb, int L0, int L1, int L2, int L3, int L4, cudaStream_t s) {
   WavTc* wt = static_cast<WavTc*>(h->wavtc);
   if (!wt) return ls_fail(h, LS_EUNSUPPORTED, "tensor-core WavEncoder not initialised");
-  const int t1 = (L1 + C1_TILE - 1) / C1_TILE, t2 = (L2 + 127) / 128, t3 = (L3 + 127) / 128;
+  const int t1 = (L1 + C1_SPAN - 1) / C1_SPAN, t2 = (L2 + 127) / 128, t3 = (L3 + 127) / 128;
   const size_t need_part = (size_t)nb * std::max(std::max(32 * t1, 64 * t2), 128 * t3), need_stats = (size_t)nb * 128;
   if (wt->v2_part_elems < need_part || wt->v2_stats_elems < need_stats) {
     if (wt->v2_part) cudaFree(wt->v2_part);
