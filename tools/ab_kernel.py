@@ -14,10 +14,11 @@ for r in range(rounds):
     for lib in libs:
         env = dict(os.environ, LS_B200_LIB=os.path.abspath(lib))
         out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "20", "--warmup", "5",
-                              "--no-cpu-baseline"], env=env, capture_output=True, text=True).stdout.strip().splitlines()[-1]
+                              "--no-cpu-baseline"] + (["--min-seconds", os.environ["AB_MIN_SECONDS"]] if "AB_MIN_SECONDS" in os.environ else []), env=env, capture_output=True, text=True).stdout.strip().splitlines()[-1]
         d = json.loads(out)
-        res[lib].append((d["roofline"]["kernel_ms"], d["roofline"]["kernel_ms_min"], d["value"], d["clocks"]["sm_mhz"]))
-        print(os.path.basename(lib), "kernel_ms %.3f min %.3f value %.1f clk %s" % res[lib][-1], flush=True)
+        res[lib].append((d["roofline"]["kernel_ms"], d["roofline"]["kernel_ms_min"], d["value"], d["clocks"]["sm_mhz"],
+                         d["e2e"]["value"], d["clocks"].get("power_w")))
+        print(os.path.basename(lib), "kernel_ms %.3f min %.3f value %.1f clk %s e2e %.1f power %s W" % res[lib][-1], flush=True)
 for lib in libs:
-    print(os.path.basename(lib), "mean kernel_ms %.3f  mean value %.1f" % (sum(x[0] for x in res[lib]) / rounds,
-                                                                           sum(x[2] for x in res[lib]) / rounds))
+    print(os.path.basename(lib), "mean kernel_ms %.3f  mean value %.1f  mean e2e %.1f" % (
+        sum(x[0] for x in res[lib]) / rounds, sum(x[2] for x in res[lib]) / rounds, sum(x[4] for x in res[lib]) / rounds))
